@@ -1,0 +1,249 @@
+/*
+ * gibbs_oracle.c -- CPU restatement of the collapsed-Gibbs hot path (TEST INFRASTRUCTURE ONLY).
+ * See gibbs_oracle.h for the contract, the layout and the parity status.
+ *
+ * Build: oracle/Makefile  (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ * -ffp-contract=off matters: every floating-point statement below is one IEEE operation, and the
+ * device kernels use the matching __fadd_rn/__fmul_rn/__fdiv_rn/__dmul_rn/... intrinsics.
+ */
+#include "gibbs_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ Philox4x32-10 (Random123) */
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+uint32_t oracle_draw_word(uint64_t seed, uint32_t stream, uint32_t sweep, uint64_t t) {
+    uint64_t blk = t >> 2;
+    uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), sweep, stream};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t out[4];
+    oracle_philox4x32_10(ctr, key, out);
+    return out[t & 3];
+}
+
+/* ------------------------------------------------------------------ init + histogram */
+int oracle_init_z(int64_t D, const int64_t *doc_ptr, const int64_t *lab_ptr, const int32_t *lab_idx,
+                  int32_t *z, uint64_t seed, uint64_t t_base) {
+    for (int64_t d = 0; d < D; ++d) {
+        uint64_t A = (uint64_t)(lab_ptr[d + 1] - lab_ptr[d]);
+        if (A == 0) return -1;
+        for (int64_t n = doc_ptr[d]; n < doc_ptr[d + 1]; ++n) {
+            uint32_t w = oracle_draw_word(seed, 1u, 0u, t_base + (uint64_t)n);
+            z[n] = lab_idx[lab_ptr[d] + (int64_t)(((uint64_t)w * A) >> 32)];
+        }
+    }
+    return 0;
+}
+
+static int find_label(const int32_t *lab, int A, int32_t k) {
+    for (int j = 0; j < A; ++j) if (lab[j] == k) return j;
+    return -1;
+}
+
+int oracle_counts_build(int64_t D, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
+                        const int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx,
+                        int32_t K, int32_t V, int32_t ldk,
+                        int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k) {
+    memset(n_wk, 0, sizeof(int32_t) * (size_t)V * (size_t)ldk);
+    memset(n_k, 0, sizeof(int32_t) * (size_t)K);
+    memset(n_dk_act, 0, sizeof(int32_t) * (size_t)lab_ptr[D]);
+    for (int64_t d = 0; d < D; ++d) {
+        const int32_t *lab = lab_idx + lab_ptr[d];
+        int A = (int)(lab_ptr[d + 1] - lab_ptr[d]);
+        for (int64_t n = doc_ptr[d]; n < doc_ptr[d + 1]; ++n) {
+            int32_t k = z[n], v = word[n], f = freq ? freq[n] : 1;
+            int j = find_label(lab, A, k);
+            if (j < 0 || v < 0 || v >= V || k < 0 || k >= K) return -1;
+            n_wk[(size_t)v * ldk + k] += f;     /* LabeledLDA.py:92 */
+            n_dk_act[lab_ptr[d] + j] += f;      /* LabeledLDA.py:91 */
+            n_k[k] += f;                        /* LabeledLDA.py:90 */
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ exact (sequential, fp64) */
+int oracle_llda_exact_sweep(int64_t d_begin, int64_t d_end, const int64_t *doc_ptr,
+                            const int32_t *word, const int32_t *freq, int32_t *z,
+                            const int64_t *lab_ptr, const int32_t *lab_idx,
+                            int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
+                            int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
+                            uint64_t seed, uint32_t sweep, uint64_t t_base) {
+    double *cum = (double *)malloc(sizeof(double) * (size_t)(K > 0 ? K : 1));
+    if (!cum) return -2;
+    const double vbeta = (double)V * beta;                 /* LabeledLDA.py:115  self.V * self.beta */
+    for (int64_t d = d_begin; d < d_end; ++d) {            /* LabeledLDA.py:106 */
+        const int32_t *lab = lab_idx + lab_ptr[d];
+        int32_t *ndk = n_dk_act + lab_ptr[d];              /* LabeledLDA.py:107 */
+        int A = (int)(lab_ptr[d + 1] - lab_ptr[d]);
+        for (int64_t n = doc_ptr[d]; n < doc_ptr[d + 1]; ++n) {   /* LabeledLDA.py:108 */
+            int32_t v = word[n], f = freq ? freq[n] : 1, zo = z[n];
+            int jo = find_label(lab, A, zo);
+            if (jo < 0) { free(cum); return -1; }
+            n_wk[(size_t)v * ldk + zo] -= f;               /* :109 */
+            ndk[jo] -= f;                                  /* :110 */
+            n_k[zo] -= f;                                  /* :111 */
+            double run = 0.0;
+            for (int j = 0; j < A; ++j) {
+                int32_t k = lab[j];
+                double a = (double)ndk[j] + alpha;                          /* :113 */
+                double num = (double)n_wk[(size_t)v * ldk + k] + beta;      /* :114 */
+                double den = (double)n_k[k] + vbeta;                        /* :115 */
+                double q = num / den;
+                double w = a * q;                                           /* :117  (lab*a)*(num_b/den_b), lab==1 */
+                run = run + w;
+                cum[j] = run;
+            }
+            /* :118-119 replaced: inverse CDF on the unnormalised weights (see patched_reference.py) */
+            uint32_t x = oracle_draw_word(seed, 0u, sweep, t_base + (uint64_t)n);
+            double u = ((double)x + 0.5) * (1.0 / 4294967296.0);
+            double thr = u * run;
+            int jn = A - 1;
+            for (int j = 0; j < A; ++j) if (cum[j] > thr) { jn = j; break; }
+            int32_t zn = lab[jn];
+            z[n] = zn;                                     /* :121 */
+            n_wk[(size_t)v * ldk + zn] += f;               /* :123 */
+            ndk[jn] += f;                                  /* :124 */
+            n_k[zn] += f;                                  /* :125 */
+        }
+    }
+    free(cum);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ snapshot (doc-parallel, fp32) */
+
+/* Inclusive scan of x[0..31] in the order a 32-lane Kogge-Stone __shfl_up scan produces. */
+static void ks_scan32(float *x) {
+    for (int off = 1; off < 32; off <<= 1) {
+        float y[32];
+        for (int j = 0; j < 32; ++j) y[j] = (j >= off) ? x[j] + x[j - off] : x[j];
+        memcpy(x, y, sizeof(y));
+    }
+}
+
+/* One document under the snapshot schedule.  frozen n_wk / n_k are read-only; updates go to delta. */
+static int snapshot_doc(int64_t d, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
+                        int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx, int32_t ldk,
+                        float alpha_f, float beta_f, float vbeta_f,
+                        const int32_t *n_wk, int32_t *n_dk_act, const int32_t *n_k,
+                        int32_t *delta_wk, int32_t *delta_k,
+                        uint64_t seed, uint32_t sweep, uint64_t t_base,
+                        int32_t *nkb, float *cum) {
+    const int32_t *lab = lab_idx + lab_ptr[d];
+    int32_t *ndk = n_dk_act + lab_ptr[d];
+    int A = (int)(lab_ptr[d + 1] - lab_ptr[d]);
+    int nchunk = (A + 31) / 32;
+    for (int j = 0; j < A; ++j) nkb[j] = n_k[lab[j]] - ndk[j];
+    for (int64_t n = doc_ptr[d]; n < doc_ptr[d + 1]; ++n) {
+        int32_t v = word[n], f = freq ? freq[n] : 1, zo = z[n];
+        int jo = find_label(lab, A, zo);
+        if (jo < 0) return -1;
+        const int32_t *row = n_wk + (size_t)v * ldk;
+        float carry = 0.0f, total = 0.0f;
+        for (int c = 0; c < nchunk; ++c) {
+            float x[32];
+            for (int l = 0; l < 32; ++l) {
+                int j = c * 32 + l;
+                if (j < A) {
+                    int32_t self = (j == jo) ? f : 0;
+                    int32_t nd = ndk[j] - self;
+                    int32_t nw = row[lab[j]] - self;
+                    float a = (float)nd + alpha_f;
+                    float b = (float)nw + beta_f;
+                    float cc = (float)(nkb[j] + nd) + vbeta_f;
+                    float ab = a * b;
+                    x[l] = ab / cc;
+                } else {
+                    x[l] = 0.0f;
+                }
+            }
+            ks_scan32(x);
+            for (int l = 0; l < 32; ++l) {
+                int j = c * 32 + l;
+                if (j < A) cum[j] = carry + x[l];
+            }
+            if (c == nchunk - 1) total = cum[A - 1];
+            carry = carry + x[31];
+        }
+        uint32_t xw = oracle_draw_word(seed, 0u, sweep, t_base + (uint64_t)n);
+        float u = (float)(xw >> 8) * (1.0f / 16777216.0f);
+        float thr = u * total;
+        int jn = A - 1;
+        for (int j = 0; j < A; ++j) if (cum[j] > thr) { jn = j; break; }
+        if (jn != jo) {
+            int32_t zn = lab[jn];
+            z[n] = zn;
+            ndk[jo] -= f;
+            ndk[jn] += f;
+#pragma omp atomic
+            delta_wk[(size_t)v * ldk + zo] -= f;
+#pragma omp atomic
+            delta_wk[(size_t)v * ldk + zn] += f;
+#pragma omp atomic
+            delta_k[zo] -= f;
+#pragma omp atomic
+            delta_k[zn] += f;
+        }
+    }
+    return 0;
+}
+
+int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_ptr, int32_t n_blocks,
+                               const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
+                               int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx,
+                               int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
+                               int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
+                               uint64_t seed, uint32_t sweep, uint64_t t_base, int32_t n_threads) {
+    if (n_blocks < 1) n_blocks = 1;
+    if (n_threads < 1) n_threads = 1;
+    const float alpha_f = (float)alpha, beta_f = (float)beta, vbeta_f = (float)((double)V * beta);
+    size_t tab = (size_t)V * (size_t)ldk;
+    int32_t *delta_wk = (int32_t *)calloc(tab, sizeof(int32_t));
+    int32_t *delta_k = (int32_t *)calloc((size_t)K, sizeof(int32_t));
+    if (!delta_wk || !delta_k) { free(delta_wk); free(delta_k); return -2; }
+    int err = 0;
+    for (int32_t b = 0; b < n_blocks; ++b) {
+#pragma omp parallel num_threads(n_threads)
+        {
+            int32_t *nkb = (int32_t *)malloc(sizeof(int32_t) * (size_t)K);
+            float *cum = (float *)malloc(sizeof(float) * (size_t)K);
+#pragma omp for schedule(dynamic, 1)
+            for (int64_t i = b; i < n_tiles; i += n_blocks) {
+                for (int64_t d = tile_ptr[i]; d < tile_ptr[i + 1]; ++d) {
+                    int r = snapshot_doc(d, doc_ptr, word, freq, z, lab_ptr, lab_idx, ldk,
+                                         alpha_f, beta_f, vbeta_f, n_wk, n_dk_act, n_k,
+                                         delta_wk, delta_k, seed, sweep, t_base, nkb, cum);
+                    if (r) {
+#pragma omp atomic write
+                        err = r;
+                    }
+                }
+            }
+            free(nkb); free(cum);
+        }
+        /* refresh: fold the block's deltas into the tables every later block reads */
+        for (size_t i = 0; i < tab; ++i) { n_wk[i] += delta_wk[i]; delta_wk[i] = 0; }
+        for (int32_t k = 0; k < K; ++k) { n_k[k] += delta_k[k]; delta_k[k] = 0; }
+    }
+    free(delta_wk); free(delta_k);
+    return err;
+}
