@@ -207,7 +207,15 @@ static int snapshot_doc(int64_t d, const int64_t *doc_ptr, const int32_t *word, 
     return 0;
 }
 
-int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_ptr, int32_t n_blocks,
+int oracle_openmp_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 0;
+#endif
+}
+
+int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t n_blocks,
                                const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
                                int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx,
                                int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
@@ -228,7 +236,7 @@ int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_ptr, int32_t
             float *cum = (float *)malloc(sizeof(float) * (size_t)K);
 #pragma omp for schedule(dynamic, 1)
             for (int64_t i = b; i < n_tiles; i += n_blocks) {
-                for (int64_t d = tile_ptr[i]; d < tile_ptr[i + 1]; ++d) {
+                for (int64_t d = tile_rng[2 * i]; d < tile_rng[2 * i + 1]; ++d) {
                     int r = snapshot_doc(d, doc_ptr, word, freq, z, lab_ptr, lab_idx, ldk,
                                          alpha_f, beta_f, vbeta_f, n_wk, n_dk_act, n_k,
                                          delta_wk, delta_k, seed, sweep, t_base, nkb, cum);

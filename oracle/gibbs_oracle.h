@@ -58,9 +58,12 @@ int oracle_llda_exact_sweep(int64_t d_begin, int64_t d_end, const int64_t *doc_p
 
 /* One sweep of the document-parallel `snapshot` schedule in fp32: every draw reads
  * n_wk frozen at the start of its refresh block, the document's own live n_dk, and
- * n_k(frozen) + (n_dk(live) - n_dk(block start)).  Tiles i with i % n_blocks == b form block b.
+ * n_k(frozen) + (n_dk(live) - n_dk(block start)).  Tile i is the document range
+ * [tile_rng[2i], tile_rng[2i+1]) (empty ranges allowed); tiles with i % n_blocks == b form block b.
  * n_threads > 1 runs the documents of a block concurrently (the result does not depend on it). */
-int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_ptr, int32_t n_blocks,
+/* 0 when built without OpenMP, else omp_get_max_threads(). */
+int oracle_openmp_threads(void);
+int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t n_blocks,
                                const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
                                int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx,
                                int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
