@@ -16,7 +16,8 @@
  * Conventions
  *   - plain C, no torch/NumPy types; the caller owns every host buffer, the handle owns all device memory
  *   - every function returns 0 on success or a negative GIBBS_E_* code; gibbs_last_error() gives the text
- *   - calls are synchronous on return unless stated; a handle is not thread-safe
+ *   - calls are synchronous on return; a handle is not thread-safe; gibbs_load may be called again on a live handle
+ *     (same D, V, K) and re-uses its device allocations
  *   - there is NO CPU fallback: without a CUDA device gibbs_create fails with GIBBS_E_CUDA
  *
  * Corpus layout (CSR over "draws"; a draw is one (document, unique word id) pair with weight f,
@@ -53,6 +54,16 @@ extern "C" {
 #define GIBBS_MODE_EXACT     0  /* corpus-order sequential chain, fp64, live counts: bit-parity with the reference loop */
 #define GIBBS_MODE_SNAPSHOT  1  /* document-parallel, fp32, counts frozen per refresh block, integer delta table */
 
+/* Row fetch of the snapshot schedule (same arithmetic, same results):
+ *   DENSE  -- cp.async the whole ldk-wide row (or the document's topic segment) into a shared-memory ring
+ *   GATHER -- one 4-byte load per active topic (touches |label list| 32-byte sectors); label lists <= 32 only
+ *   AUTO   -- GATHER for short label lists, DENSE otherwise */
+#define GIBBS_FETCH_AUTO     0
+#define GIBBS_FETCH_DENSE    1
+#define GIBBS_FETCH_GATHER   2
+
+#define GIBBS_COMM_ID_BYTES  128
+
 typedef struct gibbs_handle gibbs_t;
 
 typedef struct {
@@ -68,17 +79,22 @@ typedef struct {
     int32_t  n_refresh;   /* snapshot mode: refresh blocks per sweep (>= 1) */
     int64_t  draw_base;   /* global index of this shard's first draw (RNG addressing across shards) */
     int64_t  tile_base;   /* global index of this shard's first tile (refresh-block assignment across shards) */
-    int32_t  tile_docs;   /* documents per tile (0 -> library default) */
-    int32_t  reserved;
+    int32_t  tile_docs;   /* documents per tile (0 -> library default 256) */
+    int32_t  row_fetch;   /* GIBBS_FETCH_*: how the snapshot kernels read n_wk[v][label list] */
 } gibbs_desc;
 
 typedef struct {
     int64_t  draws;            /* draws resampled since create */
     int64_t  sweeps;           /* completed sweeps */
-    double   last_sweep_ms;    /* CUDA-event time of the sampling kernels of the last gibbs_sweep call, per sweep */
-    double   last_merge_ms;    /* same for the delta merge */
-    int64_t  last_launches;    /* kernels launched by the last gibbs_sweep / gibbs_sweep_begin+end */
-    double   bytes_per_draw;   /* algorithmic bytes per draw of the dense-row model */
+    double   last_sweep_ms;    /* CUDA-event time of the sampling kernels of the LAST sweep of the last gibbs_sweep call */
+    double   last_merge_ms;    /* same for the delta all-reduce + merge */
+    double   last_call_ms;     /* CUDA-event time of the whole last gibbs_sweep call (all its sweeps) */
+    int64_t  last_launches;    /* kernels launched per sweep by the last gibbs_sweep call */
+    double   bytes_per_draw;   /* algorithmic bytes per draw of the row fetch in use */
+    double   bytes_per_draw_dense;
+    double   bytes_per_draw_gather;
+    int32_t  row_fetch;        /* GIBBS_FETCH_DENSE or GIBBS_FETCH_GATHER: the one that carries most draws */
+    int32_t  reserved;
     int32_t  ldk;
     int32_t  max_active;       /* max |label list| over documents */
     int64_t  changed;          /* draws whose topic changed in the last sweep */
@@ -100,17 +116,19 @@ void gibbs_destroy(gibbs_t *h);
 int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
                const int32_t *z_init, const int64_t *lab_ptr, const int32_t *lab_idx, const int32_t *seg);
 
-/* n_sweeps full sweeps (sampling kernels + delta merge).  Single shard only. */
+/* n_sweeps full sweeps, enqueued back to back on the handle's stream; synchronous on return.
+ * Per refresh block: sampling kernels -> [all-reduce of the delta table over the communicator] -> merge
+ * (n_wk += delta, n_k += column sums, delta = 0). */
 int gibbs_sweep(gibbs_t *h, int32_t n_sweeps);
 
-/* Multi-shard protocol, one call sequence per refresh block b = 0 .. n_refresh-1:
- *   gibbs_sweep_begin(h, b)   -- sample this shard's tiles of block b against the frozen table into the delta table
- *   (caller all-reduces the buffer returned by gibbs_delta_buffer over all shards, e.g. NCCL sum, int32)
- *   gibbs_sweep_end(h, b)     -- n_wk += delta, n_k += column sums, delta = 0; after the last block: sweep counter++ */
-int gibbs_sweep_begin(gibbs_t *h, int32_t block);
-int gibbs_sweep_end  (gibbs_t *h, int32_t block);
-/* Device pointer + element count (int32) of the delta table, for the caller's collective. */
-int gibbs_delta_buffer(gibbs_t *h, void **dev_ptr, int64_t *n_elems);
+/* Multi-GPU (one process per GPU; SURVEY.md §8e -- the reference has no counterpart).  Documents are sharded by the
+ * caller: each rank creates its handle with its shard's D, draw_base and tile_base, calls gibbs_comm_init BEFORE
+ * gibbs_load, and from then on gibbs_load all-reduces the initial histograms and every refresh block of gibbs_sweep
+ * all-reduces the int32 delta table (ncclAllReduce, sum) on the handle's stream.  Every rank then holds identical
+ * n_wk / n_k, and the chain is bit-identical to the single-GPU run of the concatenated corpus.
+ * The 128-byte id comes from gibbs_comm_unique_id on one rank and is distributed by the caller. */
+int gibbs_comm_unique_id(char *id /* [GIBBS_COMM_ID_BYTES] */);
+int gibbs_comm_init(gibbs_t *h, int32_t nranks, int32_t rank, const char *id /* [GIBBS_COMM_ID_BYTES] */);
 /* Stream all of the handle's work is enqueued on (cudaStream_t as void*). */
 int gibbs_stream(gibbs_t *h, void **stream);
 
@@ -118,6 +136,11 @@ int gibbs_stream(gibbs_t *h, void **stream);
 int gibbs_get_state(gibbs_t *h, int32_t *z, int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k);
 /* Replace z (global topic ids) and rebuild all counts. */
 int gibbs_set_z(gibbs_t *h, const int32_t *z);
+
+/* n_wk[word[i]][topic[i]] += count[i] for i < n; n_k and n_dk are left alone.  Exists for ONE reference quirk:
+ * SubLDA.__init__ (CascadeLDA.py:382-385) iterates (id, freq) tuples, so `n_k_v[z, (id, freq)] += f` also credits
+ * column `freq`; a drop-in CascadeLDA must start from the same table. */
+int gibbs_add_counts(gibbs_t *h, int64_t n, const int32_t *word, const int32_t *topic, const int32_t *count);
 
 /* phi[K][V] (C order, fp64).  smoothed != 0: (n_kv + beta) / (n_k + V*beta)  (LabeledLDA.py:231-234)
  *                             smoothed == 0: n_kv / sum_v n_kv, NaN rows for empty topics (CascadeLDA.py:394-395).
@@ -127,7 +150,13 @@ int gibbs_emit_phi(gibbs_t *h, double *phi_KV, int32_t smoothed);
  * (HSLDA.py:148-149). */
 int gibbs_emit_theta(gibbs_t *h, double *theta_DK, int32_t smoothed);
 
+/* theta over the label lists only: theta_act[lab_ptr[d] + j] = theta[d][lab_idx[lab_ptr[d] + j]]; every other entry of
+ * the dense matrix is 0.  Use this at scale (D*K doubles do not fit anywhere at 1M x 500). */
+int gibbs_emit_theta_csr(gibbs_t *h, double *theta_act, int32_t smoothed);
+
 int gibbs_stats(gibbs_t *h, gibbs_stats_t *out);
+/* Free the handle's staging memory (upload / export scratch); it is re-allocated on demand. */
+int gibbs_trim(gibbs_t *h);
 int gibbs_set_sweep_counter(gibbs_t *h, uint32_t sweep);
 
 /* HSLDA.sample_z state (HSLDA.py:222-231): eta[L][K], per-document label lists come from lab_ptr/lab_idx of

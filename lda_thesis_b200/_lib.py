@@ -14,18 +14,23 @@ LIB_PATH = os.path.join(_HERE, "libgibbs_b200.so")
 KIND_LLDA, KIND_HSLDA = 0, 1
 MODE_EXACT, MODE_SNAPSHOT = 0, 1
 MODES = {"exact": MODE_EXACT, "snapshot": MODE_SNAPSHOT}
+FETCH = {"auto": 0, "dense": 1, "gather": 2}
+FETCH_NAME = {1: "dense", 2: "gather"}
+COMM_ID_BYTES = 128
 
 
 class GibbsDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("mode", C.c_int32), ("D", C.c_int64), ("V", C.c_int32), ("K", C.c_int32),
                 ("alpha", C.c_double), ("beta", C.c_double), ("seed", C.c_uint64), ("device", C.c_int32),
                 ("n_refresh", C.c_int32), ("draw_base", C.c_int64), ("tile_base", C.c_int64),
-                ("tile_docs", C.c_int32), ("reserved", C.c_int32)]
+                ("tile_docs", C.c_int32), ("row_fetch", C.c_int32)]
 
 
 class GibbsStats(C.Structure):
     _fields_ = [("draws", C.c_int64), ("sweeps", C.c_int64), ("last_sweep_ms", C.c_double),
-                ("last_merge_ms", C.c_double), ("last_launches", C.c_int64), ("bytes_per_draw", C.c_double),
+                ("last_merge_ms", C.c_double), ("last_call_ms", C.c_double), ("last_launches", C.c_int64),
+                ("bytes_per_draw", C.c_double), ("bytes_per_draw_dense", C.c_double),
+                ("bytes_per_draw_gather", C.c_double), ("row_fetch", C.c_int32), ("reserved", C.c_int32),
                 ("ldk", C.c_int32), ("max_active", C.c_int32), ("changed", C.c_int64), ("device_bytes", C.c_int64)]
 
 
@@ -55,12 +60,14 @@ def load_library():
     lib.gibbs_destroy.restype = None
     lib.gibbs_load.argtypes = [vp, _p(i64), _p(i32), _p(i32), _p(i32), _p(i64), _p(i32), _p(i32)]
     lib.gibbs_sweep.argtypes = [vp, i32]
-    lib.gibbs_sweep_begin.argtypes = [vp, i32]
-    lib.gibbs_sweep_end.argtypes = [vp, i32]
-    lib.gibbs_delta_buffer.argtypes = [vp, _p(vp), _p(i64)]
+    lib.gibbs_comm_unique_id.argtypes = [C.c_char_p]
+    lib.gibbs_comm_init.argtypes = [vp, i32, i32, C.c_char_p]
+    lib.gibbs_emit_theta_csr.argtypes = [vp, _p(dbl), i32]
+    lib.gibbs_trim.argtypes = [vp]
     lib.gibbs_stream.argtypes = [vp, _p(vp)]
     lib.gibbs_get_state.argtypes = [vp, _p(i32), _p(i32), _p(i32), _p(i32)]
     lib.gibbs_set_z.argtypes = [vp, _p(i32)]
+    lib.gibbs_add_counts.argtypes = [vp, i64, _p(i32), _p(i32), _p(i32)]
     lib.gibbs_emit_phi.argtypes = [vp, _p(dbl), i32]
     lib.gibbs_emit_theta.argtypes = [vp, _p(dbl), i32]
     lib.gibbs_stats.argtypes = [vp, _p(GibbsStats)]
@@ -69,8 +76,8 @@ def load_library():
     lib.gibbs_test_chains.argtypes = [i32, i32, i32, dbl, _p(dbl), i64, _p(i64), _p(i32), _p(i32), _p(i32), i32, i32,
                                       u64, _p(dbl)]
     lib.gibbs_philox_kat.argtypes = [i32, i32, _p(C.c_uint32), _p(C.c_uint32), _p(C.c_uint32)]
-    for name in ("gibbs_create", "gibbs_load", "gibbs_sweep", "gibbs_sweep_begin", "gibbs_sweep_end",
-                 "gibbs_delta_buffer", "gibbs_stream", "gibbs_get_state", "gibbs_set_z", "gibbs_emit_phi",
+    for name in ("gibbs_create", "gibbs_load", "gibbs_sweep", "gibbs_comm_unique_id", "gibbs_comm_init",
+                 "gibbs_emit_theta_csr", "gibbs_trim", "gibbs_stream", "gibbs_get_state", "gibbs_set_z", "gibbs_add_counts", "gibbs_emit_phi",
                  "gibbs_emit_theta", "gibbs_stats", "gibbs_set_sweep_counter", "gibbs_hslda_set",
                  "gibbs_test_chains", "gibbs_philox_kat"):
         getattr(lib, name).restype = C.c_int
@@ -120,7 +127,7 @@ class GibbsSampler(object):
     """One device-resident corpus shard + its count tables.  Thin object wrapper over the C-ABI."""
 
     def __init__(self, D, V, K, alpha, beta, seed=0, mode="snapshot", kind=KIND_LLDA, device=0, n_refresh=1,
-                 draw_base=0, tile_base=0, tile_docs=0):
+                 draw_base=0, tile_base=0, tile_docs=0, row_fetch="auto"):
         lib = load_library()
         self._lib = lib
         self._h = C.c_void_p()
@@ -130,7 +137,7 @@ class GibbsSampler(object):
         desc = GibbsDesc(kind=kind, mode=MODES[mode], D=self.D, V=self.V, K=self.K, alpha=float(alpha),
                          beta=float(beta), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, device=int(device),
                          n_refresh=self.n_refresh, draw_base=int(draw_base), tile_base=int(tile_base),
-                         tile_docs=int(tile_docs), reserved=0)
+                         tile_docs=int(tile_docs), row_fetch=FETCH[row_fetch])
         _check(lib.gibbs_create(C.byref(self._h), C.byref(desc)), "gibbs_create")
         self.N = 0
         self.n_lab = 0
@@ -172,16 +179,18 @@ class GibbsSampler(object):
     def sweep(self, n=1):
         _check(self._lib.gibbs_sweep(self._h, int(n)), "gibbs_sweep")
 
-    def sweep_begin(self, block=0):
-        _check(self._lib.gibbs_sweep_begin(self._h, int(block)), "gibbs_sweep_begin")
+    def comm_init(self, nranks, rank, uid):
+        """Join the NCCL communicator (before load).  uid: the 128 bytes of comm_unique_id() from rank 0."""
+        uid = bytes(uid)
+        if len(uid) != COMM_ID_BYTES:
+            raise ValueError("uid must be %d bytes" % COMM_ID_BYTES)
+        _check(self._lib.gibbs_comm_init(self._h, int(nranks), int(rank), uid), "gibbs_comm_init")
 
-    def sweep_end(self, block=0):
-        _check(self._lib.gibbs_sweep_end(self._h, int(block)), "gibbs_sweep_end")
+    def row_fetch(self):
+        return FETCH_NAME[self.stats()["row_fetch"]]
 
-    def delta_buffer(self):
-        ptr, n = C.c_void_p(), C.c_int64()
-        _check(self._lib.gibbs_delta_buffer(self._h, C.byref(ptr), C.byref(n)), "gibbs_delta_buffer")
-        return ptr.value, n.value
+    def trim(self):
+        _check(self._lib.gibbs_trim(self._h), "gibbs_trim")
 
     def stream(self):
         s = C.c_void_p()
@@ -203,15 +212,51 @@ class GibbsSampler(object):
         out["z"], out["n_wk"], out["n_dk_act"], out["n_k"] = zb, wb, db, kb
         return out
 
+    def alloc_state_buffers(self, pinned=False, n_wk=True):
+        """Host buffers for get_state_into; pinned=True page-locks them (torch is only the allocator)."""
+        shapes = {"z": (self.N,), "n_dk_act": (self.n_lab,), "n_k": (self.K,)}
+        if n_wk:
+            shapes["n_wk"] = (self.V, self.K)
+        out = {}
+        if pinned:
+            import torch
+            self._pinned = getattr(self, "_pinned", [])
+            for k, shp in shapes.items():
+                t = torch.empty(shp, dtype=torch.int32).pin_memory()
+                self._pinned.append(t)
+                out[k] = t.numpy()
+        else:
+            for k, shp in shapes.items():
+                out[k] = np.empty(shp, dtype=np.int32)
+        return out
+
+    def get_state_into(self, bufs):
+        g = lambda k: _ptr(bufs[k], C.c_int32) if k in bufs else None
+        _check(self._lib.gibbs_get_state(self._h, g("z"), g("n_wk"), g("n_dk_act"), g("n_k")), "gibbs_get_state")
+        return bufs
+
     def set_z(self, z):
         z = _arr(z, np.int32)
         if z.shape[0] != self.N:
             raise ValueError("z must have one entry per draw")
         _check(self._lib.gibbs_set_z(self._h, _ptr(z, C.c_int32)), "gibbs_set_z")
 
+    def add_counts(self, word, topic, count):
+        word, topic, count = _arr(word, np.int32), _arr(topic, np.int32), _arr(count, np.int32)
+        if not (word.shape == topic.shape == count.shape):
+            raise ValueError("word, topic, count must have the same length")
+        _check(self._lib.gibbs_add_counts(self._h, word.shape[0], _ptr(word, C.c_int32), _ptr(topic, C.c_int32),
+                                          _ptr(count, C.c_int32)), "gibbs_add_counts")
+
     def emit_phi(self, smoothed=True):
         out = np.empty((self.K, self.V), dtype=np.float64)
         _check(self._lib.gibbs_emit_phi(self._h, _ptr(out, C.c_double), 1 if smoothed else 0), "gibbs_emit_phi")
+        return out
+
+    def emit_theta_csr(self, smoothed=True):
+        out = np.empty(self.n_lab, dtype=np.float64)
+        _check(self._lib.gibbs_emit_theta_csr(self._h, _ptr(out, C.c_double), 1 if smoothed else 0),
+               "gibbs_emit_theta_csr")
         return out
 
     def emit_theta(self, smoothed=True):
@@ -263,6 +308,13 @@ def philox_kat(ctr4, key2, device=0):
     _check(lib.gibbs_philox_kat(int(device), ctr4.shape[0], _ptr(ctr4, C.c_uint32), _ptr(key2, C.c_uint32),
                                 _ptr(out, C.c_uint32)), "gibbs_philox_kat")
     return out
+
+
+def comm_unique_id():
+    lib = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib.gibbs_comm_unique_id(buf), "gibbs_comm_unique_id")
+    return buf.raw
 
 
 def device_count():

@@ -3,9 +3,11 @@
 #include "llda_kernels.cuh"
 #include "hslda_kernels.cuh"
 #include "test_kernels.cuh"
+#include "nccl_dl.h"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -13,19 +15,17 @@
 // ---------------------------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            char buf_[512];                                                                        \
-            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
-                     __FILE__, __LINE__);                                                          \
-            return fail(e_ == cudaErrorMemoryAllocation ? GIBBS_E_NOMEM : GIBBS_E_CUDA, buf_);     \
-        }                                                                                          \
-    } while (0)
+static int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    return fail(e == cudaErrorMemoryAllocation ? GIBBS_E_NOMEM : GIBBS_E_CUDA, buf);
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call, __FILE__, __LINE__); } while (0)
+#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+#define NCK(call) do { int r_ = (call); if (r_ != 0) { char b_[256]; snprintf(b_, sizeof b_, "%s failed: %s", #call, nccl_dl::error_string(r_)); return fail(GIBBS_E_CUDA, b_); } } while (0)
 
 extern "C" const char *gibbs_last_error(void) { return g_err.c_str(); }
-extern "C" const char *gibbs_version(void) { return "gibbs_b200 0.1 (sm_100a)"; }
+extern "C" const char *gibbs_version(void) { return "gibbs_b200 0.2 (sm_100a)"; }
 extern "C" int gibbs_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -35,26 +35,38 @@ extern "C" int gibbs_device_count(void) {
 
 // ---------------------------------------------------------------------------------------------- handle
 struct DocList { long long off = 0, len = 0; };   // range inside doc_list
-static const int N_BINS = 7;                       // A<=8, <=16, <=32, <=64, <=128, <=256, <=512
-static const int BIN_CAP[N_BINS] = {8, 16, 32, 64, 128, 256, 512};
+static const int N_BINS = 8;                       // label-list length <= 4, 8, 16, 32, 64, 128, 256, 512
+static const int BIN_CAP[N_BINS] = {4, 8, 16, 32, 64, 128, 256, 512};
+static const int GATHER_BINS = 4;                  // bins 0..3 (<= 32 labels) can use the masked-gather kernel
+
+// Device buffer that only ever grows: gibbs_load on a live handle re-uses the previous allocation.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;     // elements
+};
 
 struct gibbs_handle {
     gibbs_desc desc{};
     int ldk = 0, sm_count = 0, max_active = 0, row_ints = 0;
     long long N = 0, n_lab = 0;
-    bool loaded = false;
+    bool loaded = false, has_seg = false;
     uint32_t sweep = 0;
     cudaStream_t stream = nullptr;
     // corpus
-    long long *doc_ptr = nullptr, *lab_ptr = nullptr;
-    int *lab_idx = nullptr, *seg = nullptr, *doc_list = nullptr;
-    int2 *rec = nullptr;
+    DevBuf<long long> doc_ptr, lab_ptr;
+    DevBuf<int> lab_idx, seg, doc_list;
+    DevBuf<int2> rec;
     // counts
-    int *n_wk = nullptr, *delta_wk = nullptr, *n_k = nullptr, *n_dk_act = nullptr;
-    unsigned long long *counters = nullptr;   // [0] work counter, [1] changed
-    int *err_flag = nullptr;
-    std::vector<DocList> lists;               // [block * N_BINS + bin]
-    std::vector<long long> h_doc_ptr, h_lab_ptr;
+    DevBuf<int> n_wk, delta_wk, n_k, n_dk_act, colsum;
+    DevBuf<unsigned long long> counters;   // [0] work counter, [1] changed
+    DevBuf<int> err_flag;
+    DevBuf<unsigned char> scratch;         // uploads, z export, phi/theta staging
+    std::vector<DocList> lists;            // [block * N_BINS + bin]
+    long long bin_draws[N_BINS] = {0};
+    // multi-GPU
+    void *comm = nullptr;
+    int nranks = 1, rank = 0;
     // hslda
     HsldaState hs{};
     // stats
@@ -64,21 +76,40 @@ struct gibbs_handle {
 };
 
 template <typename T>
-static int dalloc(gibbs_handle *h, T **p, size_t n) {
-    *p = nullptr;
+static int reserve(gibbs_handle *h, DevBuf<T> &b, size_t n) {
     if (n == 0) n = 1;
-    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    if (b.cap >= n) return 0;
+    if (b.p) { cudaFree(b.p); h->dev_bytes -= b.cap * sizeof(T); b.p = nullptr; b.cap = 0; }
+    CK(cudaMalloc((void **)&b.p, n * sizeof(T)));
+    b.cap = n;
     h->dev_bytes += n * sizeof(T);
     return 0;
 }
-#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+template <typename T>
+static void release(gibbs_handle *h, DevBuf<T> &b) {
+    if (b.p) { cudaFree(b.p); h->dev_bytes -= b.cap * sizeof(T); }
+    b.p = nullptr; b.cap = 0;
+}
+
+static cudaEvent_t get_event(gibbs_handle *h, size_t i) {
+    while (h->ev.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        h->ev.push_back(e);
+    }
+    return h->ev[i];
+}
 
 extern "C" int gibbs_create(gibbs_t **out, const gibbs_desc *desc) {
     if (!out || !desc) return fail(GIBBS_E_ARG, "gibbs_create: null argument");
     *out = nullptr;
     if (desc->D < 0 || desc->V <= 0 || desc->K <= 0) return fail(GIBBS_E_ARG, "gibbs_create: D, V, K must be positive");
+    if (desc->D > 0x7fffffffLL) return fail(GIBBS_E_ARG, "gibbs_create: more than 2^31-1 documents in one shard");
     if (desc->kind != GIBBS_KIND_LLDA && desc->kind != GIBBS_KIND_HSLDA) return fail(GIBBS_E_ARG, "gibbs_create: unknown kind");
     if (desc->mode != GIBBS_MODE_EXACT && desc->mode != GIBBS_MODE_SNAPSHOT) return fail(GIBBS_E_ARG, "gibbs_create: unknown mode");
+    if (desc->row_fetch < GIBBS_FETCH_AUTO || desc->row_fetch > GIBBS_FETCH_GATHER) return fail(GIBBS_E_ARG, "gibbs_create: unknown row_fetch");
+    if (desc->n_refresh > 31) return fail(GIBBS_E_ARG, "gibbs_create: n_refresh too large (max 31)");
+    if (desc->kind == GIBBS_KIND_HSLDA) return fail(GIBBS_E_STATE, "gibbs_create: GIBBS_KIND_HSLDA is not implemented in this build");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -89,14 +120,16 @@ extern "C" int gibbs_create(gibbs_t **out, const gibbs_desc *desc) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, desc->device));
     if (prop.major < 10) return fail(GIBBS_E_CUDA, "gibbs_create: device is not sm_100 class; kernels are built for sm_100a only");
+    cudaStream_t stream = nullptr;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     gibbs_handle *h = new gibbs_handle();
+    h->stream = stream;
     h->desc = *desc;
     if (h->desc.n_refresh < 1) h->desc.n_refresh = 1;
     if (h->desc.mode == GIBBS_MODE_EXACT) h->desc.n_refresh = 1;
     if (h->desc.tile_docs <= 0) h->desc.tile_docs = 256;
     h->ldk = (desc->K + 31) / 32 * 32;
     h->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     *out = h;
     return 0;
 }
@@ -105,56 +138,90 @@ extern "C" void gibbs_destroy(gibbs_t *h) {
     if (!h) return;
     cudaSetDevice(h->desc.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->doc_ptr, h->lab_ptr, h->lab_idx, h->seg, h->doc_list, h->rec, h->n_wk, h->delta_wk,
-                    h->n_k, h->n_dk_act, h->counters, h->err_flag};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->comm) nccl_dl::comm_destroy(h->comm);
+    release(h, h->doc_ptr); release(h, h->lab_ptr); release(h, h->lab_idx); release(h, h->seg);
+    release(h, h->doc_list); release(h, h->rec); release(h, h->n_wk); release(h, h->delta_wk);
+    release(h, h->n_k); release(h, h->n_dk_act); release(h, h->colsum); release(h, h->counters);
+    release(h, h->err_flag); release(h, h->scratch);
     hslda_free(&h->hs);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
 }
 
+// ---------------------------------------------------------------------------------------------- multi-GPU
+extern "C" int gibbs_comm_unique_id(char *id) {
+    if (!id) return fail(GIBBS_E_ARG, "gibbs_comm_unique_id: null argument");
+    std::string why;
+    if (!nccl_dl::load(&why)) return fail(GIBBS_E_CUDA, "gibbs_comm_unique_id: " + why);
+    NCK(nccl_dl::get_unique_id(id));
+    return 0;
+}
+
+extern "C" int gibbs_comm_init(gibbs_t *h, int32_t nranks, int32_t rank, const char *id) {
+    if (!h || !id) return fail(GIBBS_E_ARG, "gibbs_comm_init: null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(GIBBS_E_ARG, "gibbs_comm_init: bad rank / nranks");
+    if (h->loaded) return fail(GIBBS_E_STATE, "gibbs_comm_init: must be called before gibbs_load (the initial counts are all-reduced there)");
+    if (h->comm) return fail(GIBBS_E_STATE, "gibbs_comm_init: communicator already initialised");
+    if (h->desc.mode != GIBBS_MODE_SNAPSHOT) return fail(GIBBS_E_STATE, "gibbs_comm_init: only the snapshot schedule shards across GPUs");
+    std::string why;
+    if (!nccl_dl::load(&why)) return fail(GIBBS_E_CUDA, "gibbs_comm_init: " + why);
+    CK(cudaSetDevice(h->desc.device));
+    NCK(nccl_dl::comm_init_rank(&h->comm, nranks, id, rank));
+    h->nranks = nranks;
+    h->rank = rank;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- load
 static int rebuild_counts(gibbs_handle *h) {
-    CK(cudaMemsetAsync(h->n_wk, 0, sizeof(int) * (size_t)h->desc.V * h->ldk, h->stream));
-    if (h->delta_wk) CK(cudaMemsetAsync(h->delta_wk, 0, sizeof(int) * (size_t)h->desc.V * h->ldk, h->stream));
-    CK(cudaMemsetAsync(h->n_k, 0, sizeof(int) * (size_t)h->desc.K, h->stream));
-    CK(cudaMemsetAsync(h->n_dk_act, 0, sizeof(int) * (size_t)std::max<long long>(h->n_lab, 1), h->stream));
+    const size_t tab = (size_t)h->desc.V * h->ldk;
+    CK(cudaMemsetAsync(h->n_wk.p, 0, sizeof(int) * tab, h->stream));
+    if (h->delta_wk.p) CK(cudaMemsetAsync(h->delta_wk.p, 0, sizeof(int) * tab, h->stream));
+    CK(cudaMemsetAsync(h->n_k.p, 0, sizeof(int) * (size_t)h->desc.K, h->stream));
+    CK(cudaMemsetAsync(h->n_dk_act.p, 0, sizeof(int) * (size_t)std::max<long long>(h->n_lab, 1), h->stream));
     if (h->desc.D > 0) {
         const long long blocks = (h->desc.D * 32 + 255) / 256;
-        counts_build_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->desc.D, h->doc_ptr, h->lab_ptr, h->lab_idx,
-                                                                     h->rec, h->ldk, h->n_wk, h->n_dk_act, h->n_k);
+        counts_build_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->desc.D, h->doc_ptr.p, h->lab_ptr.p, h->lab_idx.p,
+                                                                     h->rec.p, h->ldk, h->n_wk.p, h->n_dk_act.p, h->n_k.p);
         CK(cudaGetLastError());
+    }
+    if (h->comm) {   // every rank holds the full word-topic table: sum of all shards' histograms
+        NCK(nccl_dl::all_reduce_i32(h->n_wk.p, tab, h->comm, h->stream));
+        NCK(nccl_dl::all_reduce_i32(h->n_k.p, (size_t)h->desc.K, h->comm, h->stream));
     }
     return 0;
 }
 
 extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
                           const int32_t *z_init, const int64_t *lab_ptr, const int32_t *lab_idx, const int32_t *seg) {
-    if (!h || !doc_ptr || !word || !lab_ptr || !lab_idx) return fail(GIBBS_E_ARG, "gibbs_load: null argument");
-    if (h->loaded) return fail(GIBBS_E_STATE, "gibbs_load: handle already loaded");
+    if (!h || !doc_ptr || !lab_ptr) return fail(GIBBS_E_ARG, "gibbs_load: null argument");
     CK(cudaSetDevice(h->desc.device));
     const long long D = h->desc.D;
-    const bool hs = h->desc.kind == GIBBS_KIND_HSLDA;
+    if (doc_ptr[D] > 0 && !word) return fail(GIBBS_E_ARG, "gibbs_load: null word array");
+    if (lab_ptr[D] > 0 && !lab_idx) return fail(GIBBS_E_ARG, "gibbs_load: null lab_idx array");
+    h->loaded = false;
     // ---- host validation
     if (doc_ptr[0] != 0 || lab_ptr[0] != 0) return fail(GIBBS_E_ARG, "gibbs_load: CSR offsets must start at 0");
     int max_a = 0;
     for (long long d = 0; d < D; ++d) {
         if (doc_ptr[d + 1] < doc_ptr[d] || lab_ptr[d + 1] < lab_ptr[d]) return fail(GIBBS_E_ARG, "gibbs_load: CSR offsets must be non-decreasing");
         const long long a = lab_ptr[d + 1] - lab_ptr[d];
-        if (!hs && (a < 1 || a > BIN_CAP[N_BINS - 1])) {
+        if (a < 1 || a > BIN_CAP[N_BINS - 1]) {
             char b[160]; snprintf(b, sizeof b, "gibbs_load: document %lld has %lld active topics (supported: 1..%d)", d, a, BIN_CAP[N_BINS - 1]);
             return fail(GIBBS_E_ARG, b);
         }
         max_a = std::max<int>(max_a, (int)a);
+        for (long long q = lab_ptr[d]; q < lab_ptr[d + 1]; ++q) {
+            if (lab_idx[q] < 0 || lab_idx[q] >= h->desc.K) return fail(GIBBS_E_ARG, "gibbs_load: lab_idx out of range");
+            if (q > lab_ptr[d] && lab_idx[q] <= lab_idx[q - 1]) return fail(GIBBS_E_ARG, "gibbs_load: lab_idx must be strictly ascending inside a document");
+        }
     }
     h->N = doc_ptr[D];
     h->n_lab = lab_ptr[D];
     h->max_active = max_a;
-    const int label_space = hs ? h->hs.L_hint : h->desc.K;   // HSLDA: lab_idx are label ids, checked in hslda_set
-    if (!hs)
-        for (long long q = 0; q < h->n_lab; ++q)
-            if (lab_idx[q] < 0 || lab_idx[q] >= label_space) return fail(GIBBS_E_ARG, "gibbs_load: lab_idx out of range");
     h->row_ints = h->ldk;
+    h->has_seg = seg != nullptr;
     if (seg) {
         int mx = 0;
         for (long long d = 0; d < D; ++d) {
@@ -166,112 +233,122 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
         }
         h->row_ints = std::max(mx, 4);
     }
-    h->h_doc_ptr.assign(doc_ptr, doc_ptr + D + 1);
-    h->h_lab_ptr.assign(lab_ptr, lab_ptr + D + 1);
 
-    // ---- upload
+    // ---- device buffers (re-used when the handle is loaded again)
     const size_t tab = (size_t)h->desc.V * h->ldk;
-    TRY(dalloc(h, &h->doc_ptr, (size_t)D + 1));
-    TRY(dalloc(h, &h->lab_ptr, (size_t)D + 1));
-    TRY(dalloc(h, &h->lab_idx, (size_t)h->n_lab));
-    TRY(dalloc(h, &h->rec, (size_t)h->N));
-    TRY(dalloc(h, &h->n_wk, tab));
-    if (h->desc.mode == GIBBS_MODE_SNAPSHOT) TRY(dalloc(h, &h->delta_wk, tab));
-    TRY(dalloc(h, &h->n_k, (size_t)h->desc.K));
-    TRY(dalloc(h, &h->n_dk_act, (size_t)(hs ? D * h->desc.K : h->n_lab)));
-    TRY(dalloc(h, &h->counters, 4));
-    TRY(dalloc(h, &h->err_flag, 1));
-    CK(cudaMemcpyAsync(h->doc_ptr, doc_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->lab_ptr, lab_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->lab_idx, lab_idx, sizeof(int) * h->n_lab, cudaMemcpyHostToDevice, h->stream));
+    const size_t Nn = (size_t)std::max<long long>(h->N, 1);
+    TRY(reserve(h, h->doc_ptr, (size_t)D + 1));
+    TRY(reserve(h, h->lab_ptr, (size_t)D + 1));
+    TRY(reserve(h, h->lab_idx, (size_t)h->n_lab));
+    TRY(reserve(h, h->rec, Nn));
+    TRY(reserve(h, h->n_wk, tab));
+    if (h->desc.mode == GIBBS_MODE_SNAPSHOT) TRY(reserve(h, h->delta_wk, tab));
+    TRY(reserve(h, h->n_k, (size_t)h->desc.K));
+    TRY(reserve(h, h->n_dk_act, (size_t)h->n_lab));
+    TRY(reserve(h, h->colsum, (size_t)h->ldk));
+    TRY(reserve(h, h->counters, 4));
+    TRY(reserve(h, h->err_flag, 1));
+    TRY(reserve(h, h->doc_list, (size_t)std::max<long long>(D, 1)));
+    TRY(reserve(h, h->scratch, 3 * Nn * sizeof(int)));
+    CK(cudaMemcpyAsync(h->doc_ptr.p, doc_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->lab_ptr.p, lab_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice, h->stream));
+    if (h->n_lab) CK(cudaMemcpyAsync(h->lab_idx.p, lab_idx, sizeof(int) * h->n_lab, cudaMemcpyHostToDevice, h->stream));
     if (seg) {
-        TRY(dalloc(h, &h->seg, (size_t)2 * D));
-        CK(cudaMemcpyAsync(h->seg, seg, sizeof(int) * 2 * D, cudaMemcpyHostToDevice, h->stream));
+        TRY(reserve(h, h->seg, (size_t)2 * D));
+        CK(cudaMemcpyAsync(h->seg.p, seg, sizeof(int) * 2 * D, cudaMemcpyHostToDevice, h->stream));
     }
-    int *t_word = nullptr, *t_freq = nullptr, *t_z = nullptr;
-    CK(cudaMalloc((void **)&t_word, sizeof(int) * std::max<long long>(h->N, 1)));
-    CK(cudaMemcpyAsync(t_word, word, sizeof(int) * h->N, cudaMemcpyHostToDevice, h->stream));
-    if (freq) {
-        CK(cudaMalloc((void **)&t_freq, sizeof(int) * std::max<long long>(h->N, 1)));
+    int *t_word = reinterpret_cast<int *>(h->scratch.p), *t_freq = nullptr, *t_z = nullptr;
+    if (h->N) CK(cudaMemcpyAsync(t_word, word, sizeof(int) * h->N, cudaMemcpyHostToDevice, h->stream));
+    if (freq && h->N) {
+        t_freq = t_word + Nn;
         CK(cudaMemcpyAsync(t_freq, freq, sizeof(int) * h->N, cudaMemcpyHostToDevice, h->stream));
     }
-    if (z_init) {
-        CK(cudaMalloc((void **)&t_z, sizeof(int) * std::max<long long>(h->N, 1)));
+    if (z_init && h->N) {
+        t_z = t_word + 2 * Nn;
         CK(cudaMemcpyAsync(t_z, z_init, sizeof(int) * h->N, cudaMemcpyHostToDevice, h->stream));
     }
-    CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
     const uint2 key = make_uint2((uint32_t)h->desc.seed, (uint32_t)(h->desc.seed >> 32));
     if (D > 0) {
         const long long blocks = (D * 32 + 255) / 256;
-        if (hs)
-            hslda_prepare_records_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr, t_word, t_z, h->rec,
-                                                                                  h->desc.K, h->desc.V, key, h->desc.draw_base, h->err_flag);
-        else
-            prepare_records_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr, t_word, t_freq, t_z, h->lab_ptr,
-                                                                            h->lab_idx, h->rec, h->desc.V, key, h->desc.draw_base, h->err_flag);
+        prepare_records_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr.p, t_word, t_freq, t_z, h->lab_ptr.p,
+                                                                        h->lab_idx.p, h->rec.p, h->desc.V, key,
+                                                                        h->desc.draw_base, h->err_flag.p);
         CK(cudaGetLastError());
     }
+
+    // ---- work lists while the upload runs: [refresh block][bin by label-list length], documents in corpus order
+    const int nb = h->desc.n_refresh;
+    {
+        std::vector<long long> cnt((size_t)nb * N_BINS, 0);
+        std::vector<unsigned char> which((size_t)D);
+        for (int b = 0; b < N_BINS; ++b) h->bin_draws[b] = 0;
+        for (long long d = 0; d < D; ++d) {
+            const long long tile = h->desc.tile_base + d / h->desc.tile_docs;
+            const int b = (int)(tile % nb);
+            int bin = 0;
+            const int a = (int)(lab_ptr[d + 1] - lab_ptr[d]);
+            while (BIN_CAP[bin] < a) ++bin;
+            which[d] = (unsigned char)(b * N_BINS + bin);   // n_refresh <= 31 (gibbs_create) keeps this below 256
+            cnt[(size_t)b * N_BINS + bin]++;
+            h->bin_draws[bin] += doc_ptr[d + 1] - doc_ptr[d];
+        }
+        h->lists.assign((size_t)nb * N_BINS, DocList());
+        long long off = 0;
+        for (size_t q = 0; q < cnt.size(); ++q) { h->lists[q].off = off; h->lists[q].len = cnt[q]; off += cnt[q]; }
+        std::vector<int> flat((size_t)std::max<long long>(D, 1));
+        std::vector<long long> cur(cnt.size());
+        for (size_t q = 0; q < cnt.size(); ++q) cur[q] = h->lists[q].off;
+        for (long long d = 0; d < D; ++d) flat[(size_t)cur[which[d]]++] = (int)d;
+        CK(cudaMemcpyAsync(h->doc_list.p, flat.data(), sizeof(int) * (size_t)D, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // flat goes out of scope
+    }
     int err = 0;
-    CK(cudaMemcpyAsync(&err, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    cudaFree(t_word); if (t_freq) cudaFree(t_freq); if (t_z) cudaFree(t_z);
+    CK(cudaMemcpy(&err, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (err) return fail(GIBBS_E_ARG, "gibbs_load: inconsistent corpus (word id out of range, f outside 0..65535, or z not in the document's label list)");
 
-    // ---- work lists: [refresh block][bin by label-list length], documents in corpus order
-    const int nb = h->desc.n_refresh;
-    std::vector<std::vector<int>> tmp((size_t)nb * N_BINS);
-    for (long long d = 0; d < D; ++d) {
-        const long long tile = h->desc.tile_base + d / h->desc.tile_docs;
-        const int b = (int)(tile % nb);
-        int bin = 0;
-        if (!hs) { const int a = (int)(lab_ptr[d + 1] - lab_ptr[d]); while (BIN_CAP[bin] < a) ++bin; }
-        tmp[(size_t)b * N_BINS + bin].push_back((int)d);
-    }
-    std::vector<int> flat; flat.reserve((size_t)D);
-    h->lists.assign((size_t)nb * N_BINS, DocList());
-    for (size_t q = 0; q < tmp.size(); ++q) {
-        h->lists[q].off = (long long)flat.size();
-        h->lists[q].len = (long long)tmp[q].size();
-        flat.insert(flat.end(), tmp[q].begin(), tmp[q].end());
-    }
-    TRY(dalloc(h, &h->doc_list, flat.size()));
-    CK(cudaMemcpyAsync(h->doc_list, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, h->stream));
-
-    if (hs) {
-        TRY(hslda_rebuild_counts(h->stream, D, h->doc_ptr, h->rec, h->desc.K, h->ldk, h->desc.V, h->n_wk, h->delta_wk,
-                                 h->n_dk_act, h->n_k));
-    } else {
-        TRY(rebuild_counts(h));
-    }
+    TRY(rebuild_counts(h));
     CK(cudaStreamSynchronize(h->stream));
     h->loaded = true;
+    h->sweep = 0;
     h->st.ldk = h->ldk;
     h->st.max_active = max_a;
-    // dense-row byte model: record read 8 + z write 4 + row segment + 2 RED (8 B each way) + per-doc terms
+    // byte models: record 8 B read + 4 B z write-back, two 4-byte RMWs on the delta table, the row fetch,
+    // and per-document terms (doc_list 4, doc_ptr/lab_ptr 16, per label: id 4 + n_dk in 4 + n_dk out 4 + n_k 4)
     {
-        const double nd = D > 0 ? (double)h->N / (double)D : 1.0;
+        const double nd = D > 0 ? std::max((double)h->N / (double)D, 1.0) : 1.0;
         const double abar = D > 0 ? (double)h->n_lab / (double)D : 1.0;
-        h->st.bytes_per_draw = 16.0 + 4.0 * h->row_ints + 16.0 + (8.0 * h->row_ints + 8.0 + 4.0 * abar) / std::max(nd, 1.0);
+        const double per_doc = (20.0 + 16.0 * abar) / nd;
+        h->st.bytes_per_draw_dense = 12.0 + 4.0 * h->row_ints + 16.0 + per_doc;
+        h->st.bytes_per_draw_gather = 12.0 + 32.0 * abar + 16.0 + per_doc;
     }
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- sweeps
+static bool bin_uses_gather(const gibbs_handle *h, int bin) {
+    if (bin >= GATHER_BINS) return false;
+    if (h->desc.row_fetch == GIBBS_FETCH_DENSE) return false;
+    if (h->desc.row_fetch == GIBBS_FETCH_GATHER) return true;
+    // auto: the gather touches <= BIN_CAP sectors of 32 B per draw; the dense path streams row_ints * 4 B through
+    // shared memory.  Short label lists always gather (no staging, no ring); longer ones while they move fewer bytes.
+    return bin <= 1 || 32 * BIN_CAP[bin] <= 4 * h->row_ints;
+}
+
 template <int G, int NCH, int R>
-static int launch_snapshot(gibbs_handle *h, const SweepParams &p) {
+static int launch_dense(gibbs_handle *h, const SweepParams &p) {
     auto kern = llda_snapshot_kernel<G, NCH, R>;
     const size_t grp_bytes = (size_t)(2 * R) * 8 + (size_t)R * p.row_ints * 4;
     const int gpw = 32 / G;
     const size_t warp_bytes = grp_bytes * gpw;
     int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, (72 * 1024) / warp_bytes));
     const size_t smem = warp_bytes * wpc;
-    if (smem > 227 * 1024) return -100;   // caller retries with a shallower ring
+    if (smem > 227 * 1024) return -100;   // caller retries with a shallower ring / wider group
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
     if (occ < 1) return -100;
-    const long long groups_needed = p.n_list;
-    const long long ctas_needed = (groups_needed + (long long)wpc * gpw - 1) / ((long long)wpc * gpw);
+    const long long ctas_needed = (p.n_list + (long long)wpc * gpw - 1) / ((long long)wpc * gpw);
     const unsigned grid = (unsigned)std::min<long long>(ctas_needed, (long long)occ * h->sm_count);
     kern<<<grid, wpc * 32, smem, h->stream>>>(p);
     CK(cudaGetLastError());
@@ -280,33 +357,35 @@ static int launch_snapshot(gibbs_handle *h, const SweepParams &p) {
 }
 
 template <int G, int NCH>
-static int launch_snapshot_r(gibbs_handle *h, const SweepParams &p) {
-    int r = launch_snapshot<G, NCH, 4>(h, p);
-    if (r == -100) r = launch_snapshot<G, NCH, 2>(h, p);
-    if (r == -100) return fail(GIBBS_E_ARG, "gibbs_sweep: n_wk row segment too long for the shared-memory ring");
+static int launch_dense_r(gibbs_handle *h, const SweepParams &p) {
+    int r = launch_dense<G, NCH, 4>(h, p);
+    if (r == -100) r = launch_dense<G, NCH, 2>(h, p);
     return r;
 }
 
+template <int G, int R>
+static int launch_gather(gibbs_handle *h, const SweepParams &p) {
+    auto kern = llda_gather_kernel<G, R>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) return fail(GIBBS_E_CUDA, "gibbs_sweep: gather kernel does not fit on an SM");
+    const long long groups_per_cta = 256 / G;
+    const long long ctas_needed = (p.n_list + groups_per_cta - 1) / groups_per_cta;
+    const unsigned grid = (unsigned)std::min<long long>(ctas_needed, (long long)occ * h->sm_count);
+    kern<<<grid, 256, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    h->st.last_launches++;
+    return 0;
+}
+
 static int sample_block(gibbs_handle *h, int block) {
-    if (h->desc.kind == GIBBS_KIND_HSLDA) {
-        const DocList &dl = h->lists[(size_t)block * N_BINS];
-        if (!dl.len) return 0;
-        CK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long), h->stream));
-        int r = hslda_launch(h->stream, h->sm_count, &h->hs, h->doc_ptr, h->lab_ptr, h->lab_idx, h->rec, h->n_wk, h->delta_wk,
-                             h->n_k, h->n_dk_act, h->doc_list + dl.off, dl.len, h->counters, h->counters + 1, h->ldk,
-                             h->desc.K, (float)h->desc.beta, (float)((double)h->desc.V * h->desc.beta), h->desc.seed, h->sweep,
-                             h->desc.draw_base);
-        if (r) return fail(GIBBS_E_CUDA, std::string("hslda launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-        h->st.last_launches++;
-        return 0;
-    }
     if (h->desc.mode == GIBBS_MODE_EXACT) {
         ExactParams p{};
-        p.doc_ptr = h->doc_ptr; p.lab_ptr = h->lab_ptr; p.lab_idx = h->lab_idx; p.n_dk_act = h->n_dk_act;
-        p.rec = h->rec; p.n_wk = h->n_wk; p.n_k = h->n_k; p.d_begin = 0; p.d_end = h->desc.D; p.ldk = h->ldk;
+        p.doc_ptr = h->doc_ptr.p; p.lab_ptr = h->lab_ptr.p; p.lab_idx = h->lab_idx.p; p.n_dk_act = h->n_dk_act.p;
+        p.rec = h->rec.p; p.n_wk = h->n_wk.p; p.n_k = h->n_k.p; p.d_begin = 0; p.d_end = h->desc.D; p.ldk = h->ldk;
         p.alpha = h->desc.alpha; p.beta = h->desc.beta; p.vbeta = (double)h->desc.V * h->desc.beta;
         p.seed_lo = (uint32_t)h->desc.seed; p.seed_hi = (uint32_t)(h->desc.seed >> 32); p.sweep = h->sweep;
-        p.draw_base = h->desc.draw_base; p.changed = h->counters + 1;
+        p.draw_base = h->desc.draw_base; p.changed = h->counters.p + 1;
         llda_exact_kernel<<<1, 32, 0, h->stream>>>(p);
         CK(cudaGetLastError());
         h->st.last_launches++;
@@ -316,126 +395,96 @@ static int sample_block(gibbs_handle *h, int block) {
         const DocList &dl = h->lists[(size_t)block * N_BINS + bin];
         if (!dl.len) continue;
         SweepParams p{};
-        p.doc_ptr = h->doc_ptr; p.lab_ptr = h->lab_ptr; p.lab_idx = h->lab_idx; p.n_dk_act = h->n_dk_act;
-        p.rec = h->rec; p.n_wk = h->n_wk; p.delta_wk = h->delta_wk; p.n_k = h->n_k; p.seg = h->seg;
-        p.doc_list = h->doc_list + dl.off; p.n_list = dl.len; p.counter = h->counters; p.changed = h->counters + 1;
+        p.doc_ptr = h->doc_ptr.p; p.lab_ptr = h->lab_ptr.p; p.lab_idx = h->lab_idx.p; p.n_dk_act = h->n_dk_act.p;
+        p.rec = h->rec.p; p.n_wk = h->n_wk.p; p.delta_wk = h->delta_wk.p; p.n_k = h->n_k.p;
+        p.seg = h->has_seg ? h->seg.p : nullptr;
+        p.doc_list = h->doc_list.p + dl.off; p.n_list = dl.len; p.counter = h->counters.p; p.changed = h->counters.p + 1;
         p.ldk = h->ldk; p.row_ints = h->row_ints;
         p.alpha = (float)h->desc.alpha; p.beta = (float)h->desc.beta; p.vbeta = (float)((double)h->desc.V * h->desc.beta);
         p.seed_lo = (uint32_t)h->desc.seed; p.seed_hi = (uint32_t)(h->desc.seed >> 32); p.sweep = h->sweep;
         p.draw_base = h->desc.draw_base;
-        CK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long), h->stream));
-        switch (bin) {
-            case 0: TRY((launch_snapshot_r<8, 1>(h, p))); break;
-            case 1: TRY((launch_snapshot_r<16, 1>(h, p))); break;
-            case 2: TRY((launch_snapshot_r<32, 1>(h, p))); break;
-            case 3: TRY((launch_snapshot_r<32, 2>(h, p))); break;
-            case 4: TRY((launch_snapshot_r<32, 4>(h, p))); break;
-            case 5: TRY((launch_snapshot_r<32, 8>(h, p))); break;
-            default: TRY((launch_snapshot_r<32, 16>(h, p))); break;
+        CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), h->stream));
+        if (bin_uses_gather(h, bin)) {
+            switch (bin) {
+                case 0: TRY((launch_gather<4, 4>(h, p))); break;
+                case 1: TRY((launch_gather<8, 4>(h, p))); break;
+                case 2: TRY((launch_gather<16, 4>(h, p))); break;
+                default: TRY((launch_gather<32, 4>(h, p))); break;
+            }
+            continue;
         }
+        // dense-row path: the ring is per group, so fall back to wider groups (fewer rings per warp) for long rows
+        int r = -100;
+        if (bin <= 1) r = launch_dense_r<8, 1>(h, p);
+        if (r == -100 && bin <= 2) r = launch_dense_r<16, 1>(h, p);
+        if (r == -100 && bin <= 3) r = launch_dense_r<32, 1>(h, p);
+        if (bin == 4) r = launch_dense_r<32, 2>(h, p);
+        if (bin == 5) r = launch_dense_r<32, 4>(h, p);
+        if (bin == 6) r = launch_dense_r<32, 8>(h, p);
+        if (bin == 7) r = launch_dense_r<32, 16>(h, p);
+        if (r == -100) return fail(GIBBS_E_ARG, "gibbs_sweep: n_wk row segment too long for the shared-memory ring (K > ~28000)");
+        TRY(r);
     }
     return 0;
 }
 
 static int merge_block(gibbs_handle *h) {
     if (h->desc.mode != GIBBS_MODE_SNAPSHOT) return 0;
+    const size_t tab = (size_t)h->desc.V * h->ldk;
+    if (h->comm) NCK(nccl_dl::all_reduce_i32(h->delta_wk.p, tab, h->comm, h->stream));
     const int ldk4 = h->ldk / 4;
     int bx = std::min(256, (ldk4 + 31) / 32 * 32);
     int by = std::max(1, 256 / bx);
     dim3 block(bx, by);
-    const long long rows_per_pass = by;
-    unsigned grid = (unsigned)std::min<long long>((h->desc.V + rows_per_pass - 1) / rows_per_pass, (long long)h->sm_count * 8);
-    merge_delta_kernel<<<grid, block, 0, h->stream>>>(reinterpret_cast<int4 *>(h->n_wk), reinterpret_cast<int4 *>(h->delta_wk),
-                                                      h->n_k, h->desc.V, ldk4, h->desc.K);
+    unsigned grid = (unsigned)std::min<long long>((h->desc.V + by - 1) / by, (long long)h->sm_count * 8);
+    merge_delta_kernel<<<grid, block, 0, h->stream>>>(reinterpret_cast<int4 *>(h->n_wk.p), reinterpret_cast<int4 *>(h->delta_wk.p),
+                                                      h->n_k.p, h->desc.V, ldk4, h->desc.K);
     CK(cudaGetLastError());
     h->st.last_launches++;
     return 0;
 }
 
-static cudaEvent_t get_event(gibbs_handle *h, size_t i) {
-    while (h->ev.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
-    return h->ev[i];
-}
-
-extern "C" int gibbs_sweep_begin(gibbs_t *h, int32_t block) {
-    if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_sweep_begin: corpus not loaded");
-    if (block < 0 || block >= h->desc.n_refresh) return fail(GIBBS_E_ARG, "gibbs_sweep_begin: bad block");
-    CK(cudaSetDevice(h->desc.device));
-    if (block == 0) {
-        h->st.last_launches = 0;
-        CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(unsigned long long), h->stream));
-    }
-    CK(cudaEventRecord(get_event(h, 0), h->stream));
-    TRY(sample_block(h, block));
-    CK(cudaEventRecord(get_event(h, 1), h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    if (block == 0) h->st.last_sweep_ms = 0;
-    h->st.last_sweep_ms += ms;
-    return 0;
-}
-
-extern "C" int gibbs_sweep_end(gibbs_t *h, int32_t block) {
-    if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_sweep_end: corpus not loaded");
-    if (block < 0 || block >= h->desc.n_refresh) return fail(GIBBS_E_ARG, "gibbs_sweep_end: bad block");
-    CK(cudaSetDevice(h->desc.device));
-    CK(cudaEventRecord(get_event(h, 0), h->stream));
-    TRY(merge_block(h));
-    CK(cudaEventRecord(get_event(h, 1), h->stream));
-    if (block == h->desc.n_refresh - 1) {
-        CK(cudaMemcpyAsync(&h->st.changed, h->counters + 1, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    if (block == 0) h->st.last_merge_ms = 0;
-    h->st.last_merge_ms += ms;
-    if (block == h->desc.n_refresh - 1) { h->sweep++; h->st.sweeps++; h->st.draws += h->N; }
-    return 0;
-}
-
+// n_sweeps sweeps on the handle's stream, no host synchronisation in between.  Events: [0] call start, [1] call end,
+// then (start, mid, end) per refresh block of the LAST sweep only.
 extern "C" int gibbs_sweep(gibbs_t *h, int32_t n_sweeps) {
     if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_sweep: corpus not loaded");
     if (n_sweeps < 0) return fail(GIBBS_E_ARG, "gibbs_sweep: n_sweeps < 0");
     if (n_sweeps == 0) return 0;
     CK(cudaSetDevice(h->desc.device));
     const int nb = h->desc.n_refresh;
+    if (!get_event(h, 2 + 3 * (size_t)nb)) return fail(GIBBS_E_CUDA, "gibbs_sweep: cudaEventCreate failed");
     h->st.last_launches = 0;
-    size_t e = 0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
     for (int s = 0; s < n_sweeps; ++s) {
-        CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(unsigned long long), h->stream));
+        const bool last = s == n_sweeps - 1;
+        CK(cudaMemsetAsync(h->counters.p + 1, 0, sizeof(unsigned long long), h->stream));
         for (int b = 0; b < nb; ++b) {
-            CK(cudaEventRecord(get_event(h, e++), h->stream));
+            if (last) CK(cudaEventRecord(h->ev[2 + 3 * b], h->stream));
             TRY(sample_block(h, b));
-            CK(cudaEventRecord(get_event(h, e++), h->stream));
+            if (last) CK(cudaEventRecord(h->ev[3 + 3 * b], h->stream));
             TRY(merge_block(h));
-            CK(cudaEventRecord(get_event(h, e++), h->stream));
+            if (last) CK(cudaEventRecord(h->ev[4 + 3 * b], h->stream));
         }
         h->sweep++;
     }
-    CK(cudaMemcpyAsync(&h->st.changed, h->counters + 1, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaMemcpyAsync(&h->st.changed, h->counters.p + 1, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->st.last_call_ms = ms;
     double samp = 0, mrg = 0;
-    for (size_t q = 0; q + 2 < e + 0 && q < e; q += 3) {
-        float a = 0, b = 0;
-        CK(cudaEventElapsedTime(&a, h->ev[q], h->ev[q + 1]));
-        CK(cudaEventElapsedTime(&b, h->ev[q + 1], h->ev[q + 2]));
-        samp += a; mrg += b;
+    for (int b = 0; b < nb; ++b) {
+        float a = 0, m = 0;
+        CK(cudaEventElapsedTime(&a, h->ev[2 + 3 * b], h->ev[3 + 3 * b]));
+        CK(cudaEventElapsedTime(&m, h->ev[3 + 3 * b], h->ev[4 + 3 * b]));
+        samp += a; mrg += m;
     }
-    h->st.last_sweep_ms = samp / n_sweeps;
-    h->st.last_merge_ms = mrg / n_sweeps;
+    h->st.last_sweep_ms = samp;
+    h->st.last_merge_ms = mrg;
     h->st.last_launches /= n_sweeps;
     h->st.sweeps += n_sweeps;
     h->st.draws += (long long)n_sweeps * h->N;
-    return 0;
-}
-
-extern "C" int gibbs_delta_buffer(gibbs_t *h, void **dev_ptr, int64_t *n_elems) {
-    if (!h || !h->loaded || !dev_ptr || !n_elems) return fail(GIBBS_E_STATE, "gibbs_delta_buffer: corpus not loaded");
-    if (!h->delta_wk) return fail(GIBBS_E_STATE, "gibbs_delta_buffer: exact mode has no delta table");
-    *dev_ptr = h->delta_wk;
-    *n_elems = (int64_t)h->desc.V * h->ldk;
     return 0;
 }
 
@@ -456,27 +505,20 @@ extern "C" int gibbs_get_state(gibbs_t *h, int32_t *z, int32_t *n_wk, int32_t *n
     if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_get_state: corpus not loaded");
     CK(cudaSetDevice(h->desc.device));
     const long long D = h->desc.D;
-    int *t_z = nullptr;
     if (z && h->N > 0) {
-        CK(cudaMalloc((void **)&t_z, sizeof(int) * h->N));
+        TRY(reserve(h, h->scratch, (size_t)h->N * sizeof(int)));
+        int *t_z = reinterpret_cast<int *>(h->scratch.p);
         const long long blocks = (D * 32 + 255) / 256;
-        if (h->desc.kind == GIBBS_KIND_HSLDA)
-            hslda_export_z_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(h->N, h->rec, t_z);
-        else
-            export_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr, h->lab_ptr, h->lab_idx, h->rec, t_z);
+        export_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr.p, h->lab_ptr.p, h->lab_idx.p, h->rec.p, t_z);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(z, t_z, sizeof(int) * h->N, cudaMemcpyDeviceToHost, h->stream));
     }
     if (n_wk)
-        CK(cudaMemcpy2DAsync(n_wk, sizeof(int) * h->desc.K, h->n_wk, sizeof(int) * h->ldk, sizeof(int) * h->desc.K,
+        CK(cudaMemcpy2DAsync(n_wk, sizeof(int) * h->desc.K, h->n_wk.p, sizeof(int) * h->ldk, sizeof(int) * h->desc.K,
                              (size_t)h->desc.V, cudaMemcpyDeviceToHost, h->stream));
-    if (n_dk_act) {
-        const long long cnt = h->desc.kind == GIBBS_KIND_HSLDA ? D * h->desc.K : h->n_lab;
-        CK(cudaMemcpyAsync(n_dk_act, h->n_dk_act, sizeof(int) * cnt, cudaMemcpyDeviceToHost, h->stream));
-    }
-    if (n_k) CK(cudaMemcpyAsync(n_k, h->n_k, sizeof(int) * h->desc.K, cudaMemcpyDeviceToHost, h->stream));
+    if (n_dk_act && h->n_lab) CK(cudaMemcpyAsync(n_dk_act, h->n_dk_act.p, sizeof(int) * h->n_lab, cudaMemcpyDeviceToHost, h->stream));
+    if (n_k) CK(cudaMemcpyAsync(n_k, h->n_k.p, sizeof(int) * h->desc.K, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (t_z) cudaFree(t_z);
     return 0;
 }
 
@@ -484,27 +526,39 @@ extern "C" int gibbs_set_z(gibbs_t *h, const int32_t *z) {
     if (!h || !h->loaded || !z) return fail(GIBBS_E_STATE, "gibbs_set_z: corpus not loaded");
     CK(cudaSetDevice(h->desc.device));
     const long long D = h->desc.D;
-    int *t_z = nullptr;
-    CK(cudaMalloc((void **)&t_z, sizeof(int) * std::max<long long>(h->N, 1)));
+    TRY(reserve(h, h->scratch, (size_t)std::max<long long>(h->N, 1) * sizeof(int)));
+    int *t_z = reinterpret_cast<int *>(h->scratch.p);
     CK(cudaMemcpyAsync(t_z, z, sizeof(int) * h->N, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
     if (D > 0) {
         const long long blocks = (D * 32 + 255) / 256;
-        if (h->desc.kind == GIBBS_KIND_HSLDA)
-            hslda_set_z_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(h->N, t_z, h->rec, h->desc.K, h->err_flag);
-        else
-            set_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr, h->lab_ptr, h->lab_idx, t_z, h->rec, h->err_flag);
+        set_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr.p, h->lab_ptr.p, h->lab_idx.p, t_z, h->rec.p, h->err_flag.p);
         CK(cudaGetLastError());
     }
     int err = 0;
-    CK(cudaMemcpyAsync(&err, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&err, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(t_z);
-    if (err) return fail(GIBBS_E_ARG, "gibbs_set_z: z not in the document's label list");
-    if (h->desc.kind == GIBBS_KIND_HSLDA)
-        TRY(hslda_rebuild_counts(h->stream, D, h->doc_ptr, h->rec, h->desc.K, h->ldk, h->desc.V, h->n_wk, h->delta_wk, h->n_dk_act, h->n_k));
-    else
-        TRY(rebuild_counts(h));
+    if (err) { h->loaded = false; return fail(GIBBS_E_ARG, "gibbs_set_z: z not in the document's label list (the handle must be loaded again)"); }
+    TRY(rebuild_counts(h));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gibbs_add_counts(gibbs_t *h, int64_t n, const int32_t *word, const int32_t *topic, const int32_t *count) {
+    if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_add_counts: corpus not loaded");
+    if (n < 0 || (n > 0 && (!word || !topic || !count))) return fail(GIBBS_E_ARG, "gibbs_add_counts: null argument");
+    if (n == 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (word[i] < 0 || word[i] >= h->desc.V || topic[i] < 0 || topic[i] >= h->desc.K)
+            return fail(GIBBS_E_ARG, "gibbs_add_counts: word or topic id out of range");
+    CK(cudaSetDevice(h->desc.device));
+    TRY(reserve(h, h->scratch, 3 * (size_t)n * sizeof(int)));
+    int *t = reinterpret_cast<int *>(h->scratch.p);
+    CK(cudaMemcpyAsync(t, word, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(t + n, topic, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(t + 2 * n, count, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    add_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, t, t + n, t + 2 * n, h->ldk, h->n_wk.p);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -514,15 +568,23 @@ extern "C" int gibbs_emit_phi(gibbs_t *h, double *phi_KV, int32_t smoothed) {
     if (!h || !h->loaded || !phi_KV) return fail(GIBBS_E_STATE, "gibbs_emit_phi: corpus not loaded");
     CK(cudaSetDevice(h->desc.device));
     const int K = h->desc.K, V = h->desc.V;
-    double *d_phi = nullptr;
-    CK(cudaMalloc((void **)&d_phi, sizeof(double) * (size_t)K * V));
+    TRY(reserve(h, h->scratch, sizeof(double) * (size_t)K * V));
+    double *d_phi = reinterpret_cast<double *>(h->scratch.p);
+    const int *den = h->n_k.p;
+    if (!smoothed) {
+        // CascadeLDA.py:394-395 / HSLDA.py:151-152 divide by the row sums of n_k_v itself (they differ from n_zk when
+        // the table carries SubLDA's spurious initial counts), so sum the table's columns here
+        CK(cudaMemsetAsync(h->colsum.p, 0, sizeof(int) * h->ldk, h->stream));
+        column_sums_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->n_wk.p, h->colsum.p, V, h->ldk);
+        CK(cudaGetLastError());
+        den = h->colsum.p;
+    }
     dim3 grid((V + 31) / 32, (K + 31) / 32), block(32, 8);
-    emit_phi_kernel<<<grid, block, 0, h->stream>>>(h->n_wk, h->n_k, d_phi, V, K, h->ldk, h->desc.beta,
+    emit_phi_kernel<<<grid, block, 0, h->stream>>>(h->n_wk.p, den, d_phi, V, K, h->ldk, h->desc.beta,
                                                    (double)V * h->desc.beta, smoothed);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(phi_KV, d_phi, sizeof(double) * (size_t)K * V, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_phi);
     return 0;
 }
 
@@ -532,37 +594,54 @@ extern "C" int gibbs_emit_theta(gibbs_t *h, double *theta_DK, int32_t smoothed) 
     const long long D = h->desc.D;
     const int K = h->desc.K;
     if (D == 0) return 0;
-    double *d_th = nullptr;
-    CK(cudaMalloc((void **)&d_th, sizeof(double) * (size_t)D * K));
+    TRY(reserve(h, h->scratch, sizeof(double) * (size_t)D * K));
+    double *d_th = reinterpret_cast<double *>(h->scratch.p);
     const long long blocks = (D * 32 + 255) / 256;
-    if (h->desc.kind == GIBBS_KIND_HSLDA)
-        hslda_emit_zbar_kernel<<<(unsigned)((D * K + 255) / 256), 256, 0, h->stream>>>(D, K, h->doc_ptr, h->n_dk_act, d_th);
-    else
-        emit_theta_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->lab_ptr, h->lab_idx, h->n_dk_act, d_th, K, h->desc.alpha, smoothed);
+    emit_theta_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->lab_ptr.p, h->lab_idx.p, h->n_dk_act.p, d_th, K, h->desc.alpha, smoothed);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(theta_DK, d_th, sizeof(double) * (size_t)D * K, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_th);
+    return 0;
+}
+
+extern "C" int gibbs_emit_theta_csr(gibbs_t *h, double *theta_act, int32_t smoothed) {
+    if (!h || !h->loaded || !theta_act) return fail(GIBBS_E_STATE, "gibbs_emit_theta_csr: corpus not loaded");
+    CK(cudaSetDevice(h->desc.device));
+    const long long D = h->desc.D;
+    if (D == 0 || h->n_lab == 0) return 0;
+    TRY(reserve(h, h->scratch, sizeof(double) * (size_t)h->n_lab));
+    double *d_th = reinterpret_cast<double *>(h->scratch.p);
+    const long long blocks = (D * 32 + 255) / 256;
+    emit_theta_csr_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->lab_ptr.p, h->n_dk_act.p, d_th, h->desc.alpha, smoothed);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(theta_act, d_th, sizeof(double) * (size_t)h->n_lab, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 extern "C" int gibbs_stats(gibbs_t *h, gibbs_stats_t *out) {
     if (!h || !out) return fail(GIBBS_E_ARG, "gibbs_stats: null argument");
     h->st.device_bytes = (int64_t)h->dev_bytes;
+    // the row fetch that carries most draws decides which byte model describes the handle
+    long long gd = 0, dd = 0;
+    for (int b = 0; b < N_BINS; ++b) (bin_uses_gather(h, b) ? gd : dd) += h->bin_draws[b];
+    h->st.row_fetch = (h->desc.mode == GIBBS_MODE_SNAPSHOT && gd >= dd) ? GIBBS_FETCH_GATHER : GIBBS_FETCH_DENSE;
+    h->st.bytes_per_draw = h->st.row_fetch == GIBBS_FETCH_GATHER ? h->st.bytes_per_draw_gather : h->st.bytes_per_draw_dense;
     *out = h->st;
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------- HSLDA state
-extern "C" int gibbs_hslda_set(gibbs_t *h, int32_t L, const double *eta, const double *a_act, const double *mean_a_act,
-                               const double *alpha_beta) {
-    if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_hslda_set: corpus not loaded");
-    if (h->desc.kind != GIBBS_KIND_HSLDA) return fail(GIBBS_E_STATE, "gibbs_hslda_set: handle is not HSLDA");
-    if (L <= 0 || !eta || !a_act || !mean_a_act || !alpha_beta) return fail(GIBBS_E_ARG, "gibbs_hslda_set: null argument");
+extern "C" int gibbs_trim(gibbs_t *h) {
+    if (!h) return fail(GIBBS_E_ARG, "gibbs_trim: null handle");
     CK(cudaSetDevice(h->desc.device));
-    int r = hslda_set(h->stream, &h->hs, L, h->desc.K, h->n_lab, eta, a_act, mean_a_act, alpha_beta, h->max_active);
-    if (r) return fail(GIBBS_E_CUDA, std::string("gibbs_hslda_set: ") + cudaGetErrorString(cudaGetLastError()));
+    CK(cudaStreamSynchronize(h->stream));
+    release(h, h->scratch);
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- HSLDA state
+extern "C" int gibbs_hslda_set(gibbs_t *, int32_t, const double *, const double *, const double *, const double *) {
+    return fail(GIBBS_E_STATE, "gibbs_hslda_set: not implemented in this build");
 }
 
 // ---------------------------------------------------------------------------------------------- test chains
@@ -575,6 +654,7 @@ extern "C" int gibbs_test_chains(int32_t device, int32_t K, int32_t V, double al
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GIBBS_E_CUDA, "gibbs_test_chains: no CUDA device; this library has no CPU path");
     CK(cudaSetDevice(device));
     int r = test_chains_run(K, V, alpha, phi_KV, D_test, doc_ptr, word, freq, z_init, it, thinning, seed, th_hat);
+    if (r == 1) return fail(GIBBS_E_STATE, "gibbs_test_chains: not implemented in this build");
     if (r == -1) return fail(GIBBS_E_ARG, "gibbs_test_chains: K too large for the test kernel");
     if (r) return fail(GIBBS_E_CUDA, std::string("gibbs_test_chains: ") + cudaGetErrorString(cudaGetLastError()));
     return 0;
@@ -586,15 +666,17 @@ extern "C" int gibbs_philox_kat(int32_t device, int32_t n, const uint32_t *ctr4,
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GIBBS_E_CUDA, "gibbs_philox_kat: no CUDA device");
     CK(cudaSetDevice(device));
-    uint32_t *d_c = nullptr, *d_k = nullptr, *d_o = nullptr;
-    CK(cudaMalloc((void **)&d_c, sizeof(uint32_t) * 4 * n));
-    CK(cudaMalloc((void **)&d_k, sizeof(uint32_t) * 2 * n));
-    CK(cudaMalloc((void **)&d_o, sizeof(uint32_t) * 4 * n));
-    CK(cudaMemcpy(d_c, ctr4, sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_k, key2, sizeof(uint32_t) * 2 * n, cudaMemcpyHostToDevice));
-    philox_kat_kernel<<<(n + 127) / 128, 128>>>(n, d_c, d_k, d_o);
-    CK(cudaGetLastError());
-    CK(cudaMemcpy(out4, d_o, sizeof(uint32_t) * 4 * n, cudaMemcpyDeviceToHost));
-    cudaFree(d_c); cudaFree(d_k); cudaFree(d_o);
+    uint32_t *d = nullptr;
+    CK(cudaMalloc((void **)&d, sizeof(uint32_t) * 10 * (size_t)n));
+    uint32_t *d_c = d, *d_k = d + 4 * (size_t)n, *d_o = d + 6 * (size_t)n;
+    cudaError_t e = cudaMemcpy(d_c, ctr4, sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_k, key2, sizeof(uint32_t) * 2 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        philox_kat_kernel<<<(n + 127) / 128, 128>>>(n, d_c, d_k, d_o);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out4, d_o, sizeof(uint32_t) * 4 * n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "gibbs_philox_kat", __FILE__, __LINE__);
     return 0;
 }

@@ -225,6 +225,123 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
 }
 
 // ----------------------------------------------------------------------------------------------
+// Snapshot sweep, masked-gather row fetch (label lists of at most G <= 32 topics).
+//
+// A group of G lanes owns one document; lane j owns entry j of its label list and keeps n_dk[j] in a
+// register for the whole document.  The document is walked in chunks of G draws:
+//   * lane i of the group holds the record of draw n0+i (one coalesced 8-byte load per lane per chunk,
+//     the next chunk's records are requested one chunk ahead) and computes that draw's Philox word;
+//   * per draw, lane j needs ONE count, n_wk[v][lab_j]: a 4-byte load that touches |label list| 32-byte
+//     sectors of the row instead of the whole ldk-wide row.  The loads run R draws ahead in a register
+//     ring, so R x (warps per SM) independent sectors are in flight per lane;
+//   * weight, Kogge-Stone scan, threshold, ballot exactly as in the dense-row kernel -- the arithmetic
+//     (and therefore the oracle restatement, oracle/gibbs_oracle.c:snapshot_doc) is the same;
+//   * +-f go to the delta table with RED.ADD; changed records are written back once per chunk.
+// No shared memory, no barriers: occupancy is bounded by registers only.
+// ----------------------------------------------------------------------------------------------
+template <int G, int R>
+__global__ void __launch_bounds__(256, 3) llda_gather_kernel(const SweepParams p) {
+    static_assert(G >= 4 && G <= 32 && (G & (G - 1)) == 0, "group width");
+    static_assert(R >= 1 && R <= G && (G % R) == 0, "ring depth must divide the chunk");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int gbase = lane & ~(G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const float alpha = p.alpha, beta = p.beta, vbeta = p.vbeta;
+    const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
+    const int ldk = p.ldk;
+    const int *__restrict__ n_wk = p.n_wk;
+    unsigned n_changed = 0;
+
+    while (true) {
+        // ---- next document of this group
+        unsigned long long di = 0;
+        if (gl == 0) di = atomicAdd(p.counter, 1ull);
+        di = __shfl_sync(gmask, di, 0, G);
+        if (di >= (unsigned long long)p.n_list) break;
+        const int d = p.doc_list[di];
+        long long n0 = p.doc_ptr[d];
+        const long long n_end = p.doc_ptr[d + 1];
+        const long long lab0 = p.lab_ptr[d];
+        const int A = (int)(p.lab_ptr[d + 1] - lab0);
+        if (n0 >= n_end) continue;
+        int lab = 0, ndk = 0, nkb = 0;
+        if (gl < A) {
+            lab = p.lab_idx[lab0 + gl];
+            ndk = p.n_dk_act[lab0 + gl];
+            nkb = p.n_k[lab] - ndk;
+        }
+        int2 cur = make_int2(0, 0), nxt = make_int2(0, 0);
+        if (n0 + gl < n_end) cur = p.rec[n0 + gl];
+        if (n0 + G + gl < n_end) nxt = p.rec[n0 + G + gl];
+        int nwq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int v = __shfl_sync(gmask, cur.x, r, G);
+            nwq[r] = (gl < A && n0 + r < n_end) ? __ldg(n_wk + (size_t)v * ldk + lab) : 0;
+        }
+
+        // ---- chunks of G draws
+        while (true) {
+            const unsigned word = philox_word((uint64_t)(p.draw_base + n0 + gl), p.sweep, GIBBS_STREAM_SWEEP, key);
+            int newy = cur.y;
+            for (int i0 = 0; i0 < G; i0 += R) {
+                if (n0 + i0 >= n_end) break;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = i0 + r;
+                    const bool live = n0 + i < n_end;
+                    const int v = __shfl_sync(gmask, cur.x, i, G);
+                    const int y = __shfl_sync(gmask, cur.y, i, G);
+                    const unsigned xw = __shfl_sync(gmask, word, i, G);
+                    const int f = REC_F(y), jo = REC_J(y);
+                    const int nw_raw = nwq[r];
+                    {   // refill the ring slot with draw i + R (this chunk or the next one)
+                        const int ii = i + R;
+                        const int srcx = (ii < G) ? cur.x : nxt.x;
+                        const int v2 = __shfl_sync(gmask, srcx, ii & (G - 1), G);
+                        nwq[r] = (gl < A && n0 + ii < n_end) ? __ldg(n_wk + (size_t)v2 * ldk + lab) : 0;
+                    }
+                    float x = 0.0f;
+                    const int self = (gl == jo) ? f : 0;
+                    const int nd = ndk - self;
+                    if (gl < A) {
+                        const float a = __fadd_rn((float)nd, alpha);
+                        const float b = __fadd_rn((float)(nw_raw - self), beta);
+                        const float cc = __fadd_rn((float)(nkb + nd), vbeta);
+                        x = __fdiv_rn(__fmul_rn(a, b), cc);
+                    }
+#pragma unroll
+                    for (int off = 1; off < G; off <<= 1) {
+                        const float t = __shfl_up_sync(gmask, x, off, G);
+                        if (gl >= off) x = __fadd_rn(x, t);
+                    }
+                    const float total = __shfl_sync(gmask, x, A - 1, G);
+                    const float thr = __fmul_rn(u01_f32(xw), total);
+                    unsigned bal = __ballot_sync(gmask, (gl < A) && (x > thr));
+                    bal = (bal >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+                    const int jn = bal ? (__ffs(bal) - 1) : (A - 1);
+                    if (live && jn != jo) {
+                        if (gl == jo) { ndk -= f; atomicAdd(&p.delta_wk[(size_t)v * ldk + lab], -f); }
+                        else if (gl == jn) { ndk += f; atomicAdd(&p.delta_wk[(size_t)v * ldk + lab], f); }
+                        if (gl == i) { newy = REC_PACK(f, jn); ++n_changed; }
+                    }
+                }
+            }
+            if (newy != cur.y) p.rec[n0 + gl].y = newy;
+            n0 += G;
+            if (n0 >= n_end) break;
+            cur = nxt;
+            nxt = make_int2(0, 0);
+            if (n0 + G + gl < n_end) nxt = p.rec[n0 + G + gl];
+        }
+        if (gl < A) p.n_dk_act[lab0 + gl] = ndk;
+    }
+    n_changed = __reduce_add_sync(0xffffffffu, n_changed);
+    if (lane == 0 && n_changed) atomicAdd(p.changed, (unsigned long long)n_changed);
+}
+
+// ----------------------------------------------------------------------------------------------
 // Exact sweep: one warp walks the corpus in order with live counts in fp64, the operation order of
 // LabeledLDA.py:109-125 (restated by oracle/gibbs_oracle.c:oracle_llda_exact_sweep).
 // ----------------------------------------------------------------------------------------------
@@ -366,6 +483,12 @@ __global__ void counts_build_kernel(long long D, const long long *doc_ptr, const
     }
 }
 
+// n_wk[word][topic] += count for a COO list (duplicates accumulate).
+__global__ void add_counts_kernel(long long n, const int *word, const int *topic, const int *count, int ldk, int *n_wk) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&n_wk[(size_t)word[i] * ldk + topic[i]], count[i]);
+}
+
 // Replace z: global topic ids -> label-list index inside the existing records.
 __global__ void set_z_kernel(long long D, const long long *doc_ptr, const long long *lab_ptr, const int *lab_idx,
                              const int *z, int2 *rec, int *err) {
@@ -419,8 +542,19 @@ __global__ void merge_delta_kernel(int4 *__restrict__ n_wk, int4 *__restrict__ d
     }
 }
 
+// Column sums of the word-major table: out[k] = sum_v n_wk[v][k]  (= row sums of the reference's n_k_v).
+__global__ void column_sums_kernel(const int *__restrict__ n_wk, int *__restrict__ out, int V, int ldk) {
+    for (int k = threadIdx.x; k < ldk; k += blockDim.x) {
+        int acc = 0;
+        for (int v = blockIdx.x; v < V; v += gridDim.x) acc += n_wk[(size_t)v * ldk + k];
+        if (acc) atomicAdd(&out[k], acc);
+    }
+}
+
 // phi[k][v] from n_wk[v][k]: 32x32 tile transpose through shared memory.
-__global__ void emit_phi_kernel(const int *__restrict__ n_wk, const int *__restrict__ n_k, double *__restrict__ phi,
+// smoothed: (n + beta) / (den[k] + V*beta) with den = n_k (LabeledLDA.py:231-234);
+// otherwise n / den[k] with den = column sums of the table (CascadeLDA.py:394-395; 0/0 -> NaN as in NumPy).
+__global__ void emit_phi_kernel(const int *__restrict__ n_wk, const int *__restrict__ den_k, double *__restrict__ phi,
                                 int V, int K, int ldk, double beta, double vbeta, int smoothed) {
     __shared__ int tile[32][33];
     const int v0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
@@ -433,7 +567,7 @@ __global__ void emit_phi_kernel(const int *__restrict__ n_wk, const int *__restr
         const int k = k0 + r, v = v0 + threadIdx.x;
         if (k < K && v < V) {
             const int c = tile[threadIdx.x][r];
-            const double den = smoothed ? __dadd_rn((double)n_k[k], vbeta) : (double)n_k[k];
+            const double den = smoothed ? __dadd_rn((double)den_k[k], vbeta) : (double)den_k[k];
             const double num = smoothed ? __dadd_rn((double)c, beta) : (double)c;
             phi[(size_t)k * V + v] = __ddiv_rn(num, den);
         }
@@ -459,6 +593,25 @@ __global__ void emit_theta_kernel(long long D, const long long *lab_ptr, const i
     for (int j = lane; j < A; j += 32) {
         const double x = smoothed ? __dadd_rn((double)n_dk_act[lab0 + j], alpha) : (double)n_dk_act[lab0 + j];
         row[lab_idx[lab0 + j]] = __ddiv_rn(x, den);
+    }
+}
+
+// theta over the label lists only (the non-zero entries of LabeledLDA.py:236-239), aligned with lab_idx.
+__global__ void emit_theta_csr_kernel(long long D, const long long *lab_ptr, const int *n_dk_act, double *theta_act,
+                                      double alpha, int smoothed) {
+    const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= D) return;
+    const long long lab0 = lab_ptr[d];
+    const int A = (int)(lab_ptr[d + 1] - lab0);
+    double den = 0.0;
+    for (int j = 0; j < A; ++j) {
+        const double x = smoothed ? __dadd_rn((double)n_dk_act[lab0 + j], alpha) : (double)n_dk_act[lab0 + j];
+        den = __dadd_rn(den, x);
+    }
+    for (int j = lane; j < A; j += 32) {
+        const double x = smoothed ? __dadd_rn((double)n_dk_act[lab0 + j], alpha) : (double)n_dk_act[lab0 + j];
+        theta_act[lab0 + j] = __ddiv_rn(x, den);
     }
 }
 
