@@ -193,6 +193,33 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def run_e2e(g, host, keep, n_local, draws_total, args, barrier, allmax):
+    """Host buffers in, host state out, every step (see the module docstring)."""
+    stt = g.get_state(n_wk=False)
+    z_pin, t = pinned_like(stt["z"])
+    keep.append(t)
+    out_bufs = g.alloc_state_buffers(pinned=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = sum(host[k].nbytes for k in host) + z_pin.nbytes
+    d2h = sum(b.nbytes for b in out_bufs.values())
+    for _ in range(2):
+        g.load(host["doc_ptr"], host["word"], host["freq"], z_pin, host["lab_ptr"], host["lab_idx"])
+        g.sweep(1)
+        g.get_state_into(out_bufs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g.load(host["doc_ptr"], host["word"], host["freq"], z_pin, host["lab_ptr"], host["lab_idx"])
+        g.sweep(1)
+        g.get_state_into(out_bufs)
+        z_pin[:] = out_bufs["z"]                    # next step continues the chain from the host-side state
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    return {"value": draws_total * e2e_steps / e2e_s, "unit": "draws/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+            "path": "GibbsSampler.load (pinned host CSR + z) -> sweep(1) -> get_state (z, n_wk, n_dk, n_k)"}
+
+
 def run_repo(args):
     import torch
     import torch.distributed as dist
@@ -246,7 +273,8 @@ def run_repo(args):
     n_refresh = args.refresh
 
     g = _lib.GibbsSampler(c["D"], c["V"], c["K"], ALPHA, BETA, seed=SEED, mode="snapshot", device=local,
-                          n_refresh=n_refresh, draw_base=draw_base, tile_base=tile_base, tile_docs=tile_docs)
+                          n_refresh=n_refresh, draw_base=draw_base, tile_base=tile_base, tile_docs=tile_docs,
+                          row_fetch=args.fetch)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -289,30 +317,9 @@ def run_repo(args):
             "traffic": ncu_traffic(wl, fetch)}
 
     # ---- e2e: host buffers in, host state out, every step
-    z_host = np.empty(n_local, dtype=np.int32)
-    stt = g.get_state(n_wk=False)
-    z_pin, t = pinned_like(stt["z"])
-    keep.append(t)
-    out_bufs = g.alloc_state_buffers(pinned=True)
-    e2e_steps = max(3, min(args.steps, 10))
-    h2d = sum(host[k].nbytes for k in host) + z_pin.nbytes
-    d2h = sum(b.nbytes for b in out_bufs.values())
-    for _ in range(2):
-        g.load(host["doc_ptr"], host["word"], host["freq"], z_pin, host["lab_ptr"], host["lab_idx"])
-        g.sweep(1)
-        g.get_state_into(out_bufs)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        g.load(host["doc_ptr"], host["word"], host["freq"], z_pin, host["lab_ptr"], host["lab_idx"])
-        g.sweep(1)
-        g.get_state_into(out_bufs)
-        z_pin[:] = out_bufs["z"]                    # next step continues the chain from the host-side state
-    barrier()
-    e2e_s = allmax(time.perf_counter() - t0)
-    e2e = {"value": draws_total * e2e_steps / e2e_s, "unit": "draws/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-           "path": "GibbsSampler.load (pinned host CSR + z) -> sweep(1) -> get_state (z, n_wk, n_dk, n_k)"}
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(g, host, keep, n_local, draws_total, args, barrier, allmax)
     launches = int(st["last_launches"]) * args.steps
 
     # ---- cpu baseline (rank 0, N=1 only)
@@ -356,6 +363,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "C2", "C4"])
     ap.add_argument("--refresh", type=int, default=1, help="refresh blocks per sweep (snapshot mode)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
+    ap.add_argument("--fetch", default="auto", choices=["auto", "dense", "gather"], help="row fetch of the sampling kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
