@@ -259,21 +259,19 @@ def run_repo(args):
     wl = args.workload or "C2"
     c, desc = build_workload(wl, rank, world)
     n_local = int(c["doc_ptr"][-1])
-    # global draw / tile offsets of this shard (RNG addressing and refresh-block assignment across shards)
+    # global id of this shard's first document (RNG addressing and refresh-block assignment across shards)
     tile_docs = 256
     if world > 1:
-        sizes = torch.zeros(world, 2, dtype=torch.int64, device="cuda")
-        sizes[rank, 0] = n_local
-        sizes[rank, 1] = (c["D"] + tile_docs - 1) // tile_docs
+        sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+        sizes[rank] = c["D"]
         dist.all_reduce(sizes)
-        sizes = sizes.cpu().numpy()
-        draw_base, tile_base = int(sizes[:rank, 0].sum()), int(sizes[:rank, 1].sum())
+        doc_base = int(sizes.cpu().numpy()[:rank].sum())
     else:
-        draw_base = tile_base = 0
+        doc_base = 0
     n_refresh = args.refresh
 
     g = _lib.GibbsSampler(c["D"], c["V"], c["K"], ALPHA, BETA, seed=SEED, mode="snapshot", device=local,
-                          n_refresh=n_refresh, draw_base=draw_base, tile_base=tile_base, tile_docs=tile_docs,
+                          n_refresh=n_refresh, doc_base=doc_base, tile_docs=tile_docs,
                           row_fetch=args.fetch)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)

@@ -55,9 +55,11 @@ extern "C" {
 #define GIBBS_MODE_SNAPSHOT  1  /* document-parallel, fp32, counts frozen per refresh block, integer delta table */
 
 /* Row fetch of the snapshot schedule (same arithmetic, same results):
- *   DENSE  -- cp.async the whole ldk-wide row (or the document's topic segment) into a shared-memory ring
- *   GATHER -- one 4-byte load per active topic (touches |label list| 32-byte sectors); label lists <= 32 only
- *   AUTO   -- GATHER for short label lists, DENSE otherwise */
+ *   DENSE  -- a group of lanes per document; cp.async of the whole ldk-wide row (or the document's topic segment)
+ *             into a shared-memory ring
+ *   GATHER -- one 4-byte load per active topic (touches |label list| 32-byte sectors): thread-per-document kernel for
+ *             label lists <= 8, group-per-document kernels for <= 32; longer lists always use DENSE
+ *   AUTO   -- GATHER where it moves fewer bytes than the row, DENSE otherwise */
 #define GIBBS_FETCH_AUTO     0
 #define GIBBS_FETCH_DENSE    1
 #define GIBBS_FETCH_GATHER   2
@@ -77,8 +79,10 @@ typedef struct {
     uint64_t seed;        /* Philox key */
     int32_t  device;      /* CUDA device ordinal */
     int32_t  n_refresh;   /* snapshot mode: refresh blocks per sweep (>= 1) */
-    int64_t  draw_base;   /* global index of this shard's first draw (RNG addressing across shards) */
-    int64_t  tile_base;   /* global index of this shard's first tile (refresh-block assignment across shards) */
+    int64_t  doc_base;    /* global id of this shard's document 0: the RNG is addressed by (global document id, position in
+                             the document) and a document's refresh block is ((doc_base + d) / tile_docs) % n_refresh, so a
+                             chain does not depend on how documents are sharded */
+    int64_t  reserved64;
     int32_t  tile_docs;   /* documents per tile (0 -> library default 256) */
     int32_t  row_fetch;   /* GIBBS_FETCH_*: how the snapshot kernels read n_wk[v][label list] */
 } gibbs_desc;
@@ -122,7 +126,7 @@ int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *word, const in
 int gibbs_sweep(gibbs_t *h, int32_t n_sweeps);
 
 /* Multi-GPU (one process per GPU; SURVEY.md §8e -- the reference has no counterpart).  Documents are sharded by the
- * caller: each rank creates its handle with its shard's D, draw_base and tile_base, calls gibbs_comm_init BEFORE
+ * caller: each rank creates its handle with its shard's D and doc_base, calls gibbs_comm_init BEFORE
  * gibbs_load, and from then on gibbs_load all-reduces the initial histograms and every refresh block of gibbs_sweep
  * all-reduces the int32 delta table (ncclAllReduce, sum) on the handle's stream.  Every rank then holds identical
  * n_wk / n_k, and the chain is bit-identical to the single-GPU run of the concatenated corpus.

@@ -22,7 +22,7 @@ COMM_ID_BYTES = 128
 class GibbsDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("mode", C.c_int32), ("D", C.c_int64), ("V", C.c_int32), ("K", C.c_int32),
                 ("alpha", C.c_double), ("beta", C.c_double), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("n_refresh", C.c_int32), ("draw_base", C.c_int64), ("tile_base", C.c_int64),
+                ("n_refresh", C.c_int32), ("doc_base", C.c_int64), ("reserved64", C.c_int64),
                 ("tile_docs", C.c_int32), ("row_fetch", C.c_int32)]
 
 
@@ -127,7 +127,7 @@ class GibbsSampler(object):
     """One device-resident corpus shard + its count tables.  Thin object wrapper over the C-ABI."""
 
     def __init__(self, D, V, K, alpha, beta, seed=0, mode="snapshot", kind=KIND_LLDA, device=0, n_refresh=1,
-                 draw_base=0, tile_base=0, tile_docs=0, row_fetch="auto"):
+                 doc_base=0, tile_docs=0, row_fetch="auto"):
         lib = load_library()
         self._lib = lib
         self._h = C.c_void_p()
@@ -136,7 +136,7 @@ class GibbsSampler(object):
         self.n_refresh = 1 if mode == "exact" else max(1, int(n_refresh))
         desc = GibbsDesc(kind=kind, mode=MODES[mode], D=self.D, V=self.V, K=self.K, alpha=float(alpha),
                          beta=float(beta), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, device=int(device),
-                         n_refresh=self.n_refresh, draw_base=int(draw_base), tile_base=int(tile_base),
+                         n_refresh=self.n_refresh, doc_base=int(doc_base), reserved64=0,
                          tile_docs=int(tile_docs), row_fetch=FETCH[row_fetch])
         _check(lib.gibbs_create(C.byref(self._h), C.byref(desc)), "gibbs_create")
         self.N = 0

@@ -34,10 +34,10 @@ extern "C" int gibbs_device_count(void) {
 }
 
 // ---------------------------------------------------------------------------------------------- handle
-struct DocList { long long off = 0, len = 0; };   // range inside doc_list
-static const int N_BINS = 8;                       // label-list length <= 4, 8, 16, 32, 64, 128, 256, 512
-static const int BIN_CAP[N_BINS] = {4, 8, 16, 32, 64, 128, 256, 512};
-static const int GATHER_BINS = 4;                  // bins 0..3 (<= 32 labels) can use the masked-gather kernel
+struct DocList { long long off = 0, len = 0; };   // range inside the work list
+static const int N_BINS = 7;                       // label-list length <= 8, 16, 32, 64, 128, 256, 512
+static const int BIN_CAP[N_BINS] = {GIBBS_SERIAL_MAX, 16, 32, 64, 128, 256, 512};
+static const int GATHER_BINS = 3;                  // bins 0..2 (<= 32 labels) have a masked-gather kernel
 
 // Device buffer that only ever grows: gibbs_load on a live handle re-uses the previous allocation.
 template <typename T>
@@ -55,8 +55,9 @@ struct gibbs_handle {
     cudaStream_t stream = nullptr;
     // corpus
     DevBuf<long long> doc_ptr, lab_ptr;
-    DevBuf<int> lab_idx, seg, doc_list;
-    DevBuf<int2> rec;
+    DevBuf<int> lab_idx, seg;
+    DevBuf<DocDesc> work;                  // one entry per document, [refresh block][bin] segments
+    DevBuf<int2> rec;                      // draw records R (see DocDesc)
     // counts
     DevBuf<int> n_wk, delta_wk, n_k, n_dk_act, colsum;
     DevBuf<unsigned long long> counters;   // [0] work counter, [1] changed
@@ -74,6 +75,9 @@ struct gibbs_handle {
     std::vector<cudaEvent_t> ev;
     size_t dev_bytes = 0;
 };
+
+static bool bin_uses_lane(const gibbs_handle *h);
+static bool bin_uses_gather(const gibbs_handle *h, int bin);
 
 template <typename T>
 static int reserve(gibbs_handle *h, DevBuf<T> &b, size_t n) {
@@ -140,7 +144,7 @@ extern "C" void gibbs_destroy(gibbs_t *h) {
     cudaStreamSynchronize(h->stream);
     if (h->comm) nccl_dl::comm_destroy(h->comm);
     release(h, h->doc_ptr); release(h, h->lab_ptr); release(h, h->lab_idx); release(h, h->seg);
-    release(h, h->doc_list); release(h, h->rec); release(h, h->n_wk); release(h, h->delta_wk);
+    release(h, h->work); release(h, h->rec); release(h, h->n_wk); release(h, h->delta_wk);
     release(h, h->n_k); release(h, h->n_dk_act); release(h, h->colsum); release(h, h->counters);
     release(h, h->err_flag); release(h, h->scratch);
     hslda_free(&h->hs);
@@ -174,22 +178,31 @@ extern "C" int gibbs_comm_init(gibbs_t *h, int32_t nranks, int32_t rank, const c
 }
 
 // ---------------------------------------------------------------------------------------------- load
+static int column_sums(gibbs_handle *h, int *out) {
+    const int ldk4 = h->ldk / 4;
+    int bx = std::min(256, (ldk4 + 31) / 32 * 32);
+    int by = std::max(1, 256 / bx);
+    unsigned grid = (unsigned)std::min<long long>((h->desc.V + by - 1) / by, (long long)h->sm_count * 8);
+    CK(cudaMemsetAsync(out, 0, sizeof(int) * (size_t)h->desc.K, h->stream));
+    column_sums_kernel<<<grid, dim3(bx, by), 0, h->stream>>>(reinterpret_cast<const int4 *>(h->n_wk.p), out, h->desc.V, ldk4, h->desc.K);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int rebuild_counts(gibbs_handle *h) {
     const size_t tab = (size_t)h->desc.V * h->ldk;
     CK(cudaMemsetAsync(h->n_wk.p, 0, sizeof(int) * tab, h->stream));
     if (h->delta_wk.p) CK(cudaMemsetAsync(h->delta_wk.p, 0, sizeof(int) * tab, h->stream));
-    CK(cudaMemsetAsync(h->n_k.p, 0, sizeof(int) * (size_t)h->desc.K, h->stream));
     CK(cudaMemsetAsync(h->n_dk_act.p, 0, sizeof(int) * (size_t)std::max<long long>(h->n_lab, 1), h->stream));
     if (h->desc.D > 0) {
         const long long blocks = (h->desc.D * 32 + 255) / 256;
-        counts_build_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->desc.D, h->doc_ptr.p, h->lab_ptr.p, h->lab_idx.p,
-                                                                     h->rec.p, h->ldk, h->n_wk.p, h->n_dk_act.p, h->n_k.p);
+        counts_build_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->desc.D, h->work.p, h->lab_idx.p, h->rec.p, h->ldk,
+                                                                     h->n_wk.p, h->n_dk_act.p);
         CK(cudaGetLastError());
     }
-    if (h->comm) {   // every rank holds the full word-topic table: sum of all shards' histograms
-        NCK(nccl_dl::all_reduce_i32(h->n_wk.p, tab, h->comm, h->stream));
-        NCK(nccl_dl::all_reduce_i32(h->n_k.p, (size_t)h->desc.K, h->comm, h->stream));
-    }
+    // every rank holds the full word-topic table: sum of all shards' histograms
+    if (h->comm) NCK(nccl_dl::all_reduce_i32(h->n_wk.p, tab, h->comm, h->stream));
+    TRY(column_sums(h, h->n_k.p));     // n_zk = row sums of n_k_v (LabeledLDA.py:90,92 add the same f to both)
     return 0;
 }
 
@@ -217,6 +230,7 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
             if (q > lab_ptr[d] && lab_idx[q] <= lab_idx[q - 1]) return fail(GIBBS_E_ARG, "gibbs_load: lab_idx must be strictly ascending inside a document");
         }
     }
+    if (h->desc.doc_base < 0 || h->desc.doc_base + D > 0xffffffffLL) return fail(GIBBS_E_ARG, "gibbs_load: global document ids must fit 32 bits");
     h->N = doc_ptr[D];
     h->n_lab = lab_ptr[D];
     h->max_active = max_a;
@@ -234,13 +248,77 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
         h->row_ints = std::max(mx, 4);
     }
 
+    // ---- work list: one DocDesc per document in [refresh block][bin] segments; inside a segment longest first
+    // (thread-per-document segments: by label-list length, then length, so the 32 lanes of a slice are alike)
+    const int nb = h->desc.n_refresh;
+    const bool exact = h->desc.mode == GIBBS_MODE_EXACT;
+    std::vector<DocDesc> work((size_t)std::max<long long>(D, 1));
+    long long r_total = 0;
+    {
+        for (int b = 0; b < N_BINS; ++b) h->bin_draws[b] = 0;
+        h->lists.assign((size_t)nb * N_BINS, DocList());
+        if (exact) {      // corpus order, one segment
+            for (long long d = 0; d < D; ++d) {
+                DocDesc &w = work[(size_t)d];
+                w.rbase = doc_ptr[d]; w.lab0 = lab_ptr[d]; w.len = (int)(doc_ptr[d + 1] - doc_ptr[d]);
+                w.A = (int)(lab_ptr[d + 1] - lab_ptr[d]); w.stride = 1; w.doc = (int)d;
+            }
+            h->lists[0].off = 0; h->lists[0].len = D;
+            r_total = h->N;
+        } else {
+            long long max_len = 0;
+            for (long long d = 0; d < D; ++d) max_len = std::max<long long>(max_len, doc_ptr[d + 1] - doc_ptr[d]);
+            if (max_len > 0x7fffffffLL) return fail(GIBBS_E_ARG, "gibbs_load: a document has more than 2^31-1 draws");
+            std::vector<unsigned long long> keyed((size_t)D);      // (segment, sort key, doc) packed for one sort
+            const unsigned long long LB = (unsigned long long)max_len + 1;
+            if ((unsigned long long)nb * N_BINS * (GIBBS_SERIAL_MAX + 1) * LB >= (1ull << 32))
+                return fail(GIBBS_E_ARG, "gibbs_load: documents too long for the work-list sort key");
+            std::vector<long long> cnt((size_t)nb * N_BINS, 0);
+            for (long long d = 0; d < D; ++d) {
+                const long long tile = (h->desc.doc_base + d) / h->desc.tile_docs;
+                const int b = (int)(tile % nb);
+                const int a = (int)(lab_ptr[d + 1] - lab_ptr[d]);
+                int bin = 0;
+                while (BIN_CAP[bin] < a) ++bin;
+                const long long len = doc_ptr[d + 1] - doc_ptr[d];
+                const int seg_id = b * N_BINS + bin;
+                const unsigned long long arank = bin == 0 ? (unsigned long long)(GIBBS_SERIAL_MAX - a) : 0ull;
+                const unsigned long long key = ((unsigned long long)seg_id * (GIBBS_SERIAL_MAX + 1) + arank) * LB + (unsigned long long)(max_len - len);
+                keyed[(size_t)d] = (key << 32) | (unsigned long long)d;
+                cnt[(size_t)seg_id]++;
+                h->bin_draws[bin] += len;
+            }
+            std::sort(keyed.begin(), keyed.end());
+            long long off = 0;
+            for (size_t q = 0; q < cnt.size(); ++q) { h->lists[q].off = off; h->lists[q].len = cnt[q]; off += cnt[q]; }
+            for (size_t q = 0; q < cnt.size(); ++q) {
+                const int bin = (int)(q % N_BINS);
+                const bool sliced = bin == 0 && bin_uses_lane(h);
+                const long long o = h->lists[q].off, n = h->lists[q].len;
+                for (long long s0 = 0; s0 < n; s0 += 32) {
+                    const long long cntl = std::min<long long>(32, n - s0);
+                    long long mx = 0;
+                    for (long long l = 0; l < cntl; ++l) {
+                        const long long d = (long long)(keyed[(size_t)(o + s0 + l)] & 0xffffffffull);
+                        DocDesc &w = work[(size_t)(o + s0 + l)];
+                        w.lab0 = lab_ptr[d]; w.len = (int)(doc_ptr[d + 1] - doc_ptr[d]);
+                        w.A = (int)(lab_ptr[d + 1] - lab_ptr[d]); w.doc = (int)d;
+                        if (sliced) { w.rbase = r_total + l; w.stride = 32; mx = std::max<long long>(mx, w.len); }
+                        else        { w.rbase = r_total; w.stride = 1; r_total += w.len; }
+                    }
+                    if (sliced) r_total += 32 * mx;
+                }
+            }
+        }
+    }
+
     // ---- device buffers (re-used when the handle is loaded again)
     const size_t tab = (size_t)h->desc.V * h->ldk;
     const size_t Nn = (size_t)std::max<long long>(h->N, 1);
     TRY(reserve(h, h->doc_ptr, (size_t)D + 1));
     TRY(reserve(h, h->lab_ptr, (size_t)D + 1));
     TRY(reserve(h, h->lab_idx, (size_t)h->n_lab));
-    TRY(reserve(h, h->rec, Nn));
+    TRY(reserve(h, h->rec, (size_t)std::max<long long>(r_total, 1)));
     TRY(reserve(h, h->n_wk, tab));
     if (h->desc.mode == GIBBS_MODE_SNAPSHOT) TRY(reserve(h, h->delta_wk, tab));
     TRY(reserve(h, h->n_k, (size_t)h->desc.K));
@@ -248,8 +326,9 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
     TRY(reserve(h, h->colsum, (size_t)h->ldk));
     TRY(reserve(h, h->counters, 4));
     TRY(reserve(h, h->err_flag, 1));
-    TRY(reserve(h, h->doc_list, (size_t)std::max<long long>(D, 1)));
+    TRY(reserve(h, h->work, (size_t)std::max<long long>(D, 1)));
     TRY(reserve(h, h->scratch, 3 * Nn * sizeof(int)));
+    CK(cudaMemcpyAsync(h->work.p, work.data(), sizeof(DocDesc) * (size_t)D, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->doc_ptr.p, doc_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->lab_ptr.p, lab_ptr, sizeof(long long) * (D + 1), cudaMemcpyHostToDevice, h->stream));
     if (h->n_lab) CK(cudaMemcpyAsync(h->lab_idx.p, lab_idx, sizeof(int) * h->n_lab, cudaMemcpyHostToDevice, h->stream));
@@ -271,38 +350,12 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
     const uint2 key = make_uint2((uint32_t)h->desc.seed, (uint32_t)(h->desc.seed >> 32));
     if (D > 0) {
         const long long blocks = (D * 32 + 255) / 256;
-        prepare_records_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr.p, t_word, t_freq, t_z, h->lab_ptr.p,
+        prepare_records_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->work.p, h->doc_ptr.p, t_word, t_freq, t_z,
                                                                         h->lab_idx.p, h->rec.p, h->desc.V, key,
-                                                                        h->desc.draw_base, h->err_flag.p);
+                                                                        h->desc.doc_base, h->err_flag.p);
         CK(cudaGetLastError());
     }
-
-    // ---- work lists while the upload runs: [refresh block][bin by label-list length], documents in corpus order
-    const int nb = h->desc.n_refresh;
-    {
-        std::vector<long long> cnt((size_t)nb * N_BINS, 0);
-        std::vector<unsigned char> which((size_t)D);
-        for (int b = 0; b < N_BINS; ++b) h->bin_draws[b] = 0;
-        for (long long d = 0; d < D; ++d) {
-            const long long tile = h->desc.tile_base + d / h->desc.tile_docs;
-            const int b = (int)(tile % nb);
-            int bin = 0;
-            const int a = (int)(lab_ptr[d + 1] - lab_ptr[d]);
-            while (BIN_CAP[bin] < a) ++bin;
-            which[d] = (unsigned char)(b * N_BINS + bin);   // n_refresh <= 31 (gibbs_create) keeps this below 256
-            cnt[(size_t)b * N_BINS + bin]++;
-            h->bin_draws[bin] += doc_ptr[d + 1] - doc_ptr[d];
-        }
-        h->lists.assign((size_t)nb * N_BINS, DocList());
-        long long off = 0;
-        for (size_t q = 0; q < cnt.size(); ++q) { h->lists[q].off = off; h->lists[q].len = cnt[q]; off += cnt[q]; }
-        std::vector<int> flat((size_t)std::max<long long>(D, 1));
-        std::vector<long long> cur(cnt.size());
-        for (size_t q = 0; q < cnt.size(); ++q) cur[q] = h->lists[q].off;
-        for (long long d = 0; d < D; ++d) flat[(size_t)cur[which[d]]++] = (int)d;
-        CK(cudaMemcpyAsync(h->doc_list.p, flat.data(), sizeof(int) * (size_t)D, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));   // flat goes out of scope
-    }
+    CK(cudaStreamSynchronize(h->stream));   // `work` (host) goes out of scope
     int err = 0;
     CK(cudaMemcpy(&err, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (err) return fail(GIBBS_E_ARG, "gibbs_load: inconsistent corpus (word id out of range, f outside 0..65535, or z not in the document's label list)");
@@ -326,18 +379,22 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
 }
 
 // ---------------------------------------------------------------------------------------------- sweeps
+// Short label lists (bin 0): thread-per-document kernel unless the dense row fetch is forced.
+static bool bin_uses_lane(const gibbs_handle *h) {
+    return h->desc.mode == GIBBS_MODE_SNAPSHOT && h->desc.row_fetch != GIBBS_FETCH_DENSE;
+}
 static bool bin_uses_gather(const gibbs_handle *h, int bin) {
-    if (bin >= GATHER_BINS) return false;
+    if (bin >= GATHER_BINS || h->desc.mode != GIBBS_MODE_SNAPSHOT) return false;
     if (h->desc.row_fetch == GIBBS_FETCH_DENSE) return false;
-    if (h->desc.row_fetch == GIBBS_FETCH_GATHER) return true;
+    if (bin == 0 || h->desc.row_fetch == GIBBS_FETCH_GATHER) return true;
     // auto: the gather touches <= BIN_CAP sectors of 32 B per draw; the dense path streams row_ints * 4 B through
-    // shared memory.  Short label lists always gather (no staging, no ring); longer ones while they move fewer bytes.
-    return bin <= 1 || 32 * BIN_CAP[bin] <= 4 * h->row_ints;
+    // shared memory
+    return 32 * BIN_CAP[bin] <= 4 * h->row_ints;
 }
 
-template <int G, int NCH, int R>
+template <int G, int NCH, int R, bool SERIAL>
 static int launch_dense(gibbs_handle *h, const SweepParams &p) {
-    auto kern = llda_snapshot_kernel<G, NCH, R>;
+    auto kern = llda_dense_kernel<G, NCH, R, SERIAL>;
     const size_t grp_bytes = (size_t)(2 * R) * 8 + (size_t)R * p.row_ints * 4;
     const int gpw = 32 / G;
     const size_t warp_bytes = grp_bytes * gpw;
@@ -348,7 +405,7 @@ static int launch_dense(gibbs_handle *h, const SweepParams &p) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
     if (occ < 1) return -100;
-    const long long ctas_needed = (p.n_list + (long long)wpc * gpw - 1) / ((long long)wpc * gpw);
+    const long long ctas_needed = (p.n_work + (long long)wpc * gpw - 1) / ((long long)wpc * gpw);
     const unsigned grid = (unsigned)std::min<long long>(ctas_needed, (long long)occ * h->sm_count);
     kern<<<grid, wpc * 32, smem, h->stream>>>(p);
     CK(cudaGetLastError());
@@ -356,11 +413,24 @@ static int launch_dense(gibbs_handle *h, const SweepParams &p) {
     return 0;
 }
 
-template <int G, int NCH>
+template <int G, int NCH, bool SERIAL>
 static int launch_dense_r(gibbs_handle *h, const SweepParams &p) {
-    int r = launch_dense<G, NCH, 4>(h, p);
-    if (r == -100) r = launch_dense<G, NCH, 2>(h, p);
+    int r = launch_dense<G, NCH, 4, SERIAL>(h, p);
+    if (r == -100) r = launch_dense<G, NCH, 2, SERIAL>(h, p);
     return r;
+}
+
+static int launch_lane(gibbs_handle *h, const SweepParams &p) {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llda_lane_kernel, 128, 0));
+    if (occ < 1) return fail(GIBBS_E_CUDA, "gibbs_sweep: lane kernel does not fit on an SM");
+    const long long slices = (p.n_work + 31) / 32;
+    const long long ctas_needed = (slices + 3) / 4;
+    const unsigned grid = (unsigned)std::min<long long>(ctas_needed, (long long)occ * h->sm_count);
+    llda_lane_kernel<<<grid, 128, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    h->st.last_launches++;
+    return 0;
 }
 
 template <int G, int R>
@@ -370,7 +440,7 @@ static int launch_gather(gibbs_handle *h, const SweepParams &p) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) return fail(GIBBS_E_CUDA, "gibbs_sweep: gather kernel does not fit on an SM");
     const long long groups_per_cta = 256 / G;
-    const long long ctas_needed = (p.n_list + groups_per_cta - 1) / groups_per_cta;
+    const long long ctas_needed = (p.n_work + groups_per_cta - 1) / groups_per_cta;
     const unsigned grid = (unsigned)std::min<long long>(ctas_needed, (long long)occ * h->sm_count);
     kern<<<grid, 256, 0, h->stream>>>(p);
     CK(cudaGetLastError());
@@ -381,11 +451,11 @@ static int launch_gather(gibbs_handle *h, const SweepParams &p) {
 static int sample_block(gibbs_handle *h, int block) {
     if (h->desc.mode == GIBBS_MODE_EXACT) {
         ExactParams p{};
-        p.doc_ptr = h->doc_ptr.p; p.lab_ptr = h->lab_ptr.p; p.lab_idx = h->lab_idx.p; p.n_dk_act = h->n_dk_act.p;
-        p.rec = h->rec.p; p.n_wk = h->n_wk.p; p.n_k = h->n_k.p; p.d_begin = 0; p.d_end = h->desc.D; p.ldk = h->ldk;
+        p.desc = h->work.p; p.lab_idx = h->lab_idx.p; p.n_dk_act = h->n_dk_act.p;
+        p.R = h->rec.p; p.n_wk = h->n_wk.p; p.n_k = h->n_k.p; p.d_begin = 0; p.d_end = h->desc.D; p.ldk = h->ldk;
         p.alpha = h->desc.alpha; p.beta = h->desc.beta; p.vbeta = (double)h->desc.V * h->desc.beta;
         p.seed_lo = (uint32_t)h->desc.seed; p.seed_hi = (uint32_t)(h->desc.seed >> 32); p.sweep = h->sweep;
-        p.draw_base = h->desc.draw_base; p.changed = h->counters.p + 1;
+        p.doc_base = h->desc.doc_base; p.changed = h->counters.p + 1;
         llda_exact_kernel<<<1, 32, 0, h->stream>>>(p);
         CK(cudaGetLastError());
         h->st.last_launches++;
@@ -395,33 +465,36 @@ static int sample_block(gibbs_handle *h, int block) {
         const DocList &dl = h->lists[(size_t)block * N_BINS + bin];
         if (!dl.len) continue;
         SweepParams p{};
-        p.doc_ptr = h->doc_ptr.p; p.lab_ptr = h->lab_ptr.p; p.lab_idx = h->lab_idx.p; p.n_dk_act = h->n_dk_act.p;
-        p.rec = h->rec.p; p.n_wk = h->n_wk.p; p.delta_wk = h->delta_wk.p; p.n_k = h->n_k.p;
+        p.work = h->work.p + dl.off; p.n_work = dl.len;
+        p.lab_idx = h->lab_idx.p; p.n_dk_act = h->n_dk_act.p;
+        p.R = h->rec.p; p.n_wk = h->n_wk.p; p.delta_wk = h->delta_wk.p; p.n_k = h->n_k.p;
         p.seg = h->has_seg ? h->seg.p : nullptr;
-        p.doc_list = h->doc_list.p + dl.off; p.n_list = dl.len; p.counter = h->counters.p; p.changed = h->counters.p + 1;
+        p.counter = h->counters.p; p.changed = h->counters.p + 1;
         p.ldk = h->ldk; p.row_ints = h->row_ints;
         p.alpha = (float)h->desc.alpha; p.beta = (float)h->desc.beta; p.vbeta = (float)((double)h->desc.V * h->desc.beta);
         p.seed_lo = (uint32_t)h->desc.seed; p.seed_hi = (uint32_t)(h->desc.seed >> 32); p.sweep = h->sweep;
-        p.draw_base = h->desc.draw_base;
+        p.doc_base = h->desc.doc_base;
         CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), h->stream));
+        if (bin == 0 && bin_uses_lane(h)) { TRY(launch_lane(h, p)); continue; }
         if (bin_uses_gather(h, bin)) {
-            switch (bin) {
-                case 0: TRY((launch_gather<4, 4>(h, p))); break;
-                case 1: TRY((launch_gather<8, 4>(h, p))); break;
-                case 2: TRY((launch_gather<16, 4>(h, p))); break;
-                default: TRY((launch_gather<32, 4>(h, p))); break;
-            }
+            if (bin == 1) TRY((launch_gather<16, 4>(h, p)));
+            else          TRY((launch_gather<32, 4>(h, p)));
             continue;
         }
         // dense-row path: the ring is per group, so fall back to wider groups (fewer rings per warp) for long rows
         int r = -100;
-        if (bin <= 1) r = launch_dense_r<8, 1>(h, p);
-        if (r == -100 && bin <= 2) r = launch_dense_r<16, 1>(h, p);
-        if (r == -100 && bin <= 3) r = launch_dense_r<32, 1>(h, p);
-        if (bin == 4) r = launch_dense_r<32, 2>(h, p);
-        if (bin == 5) r = launch_dense_r<32, 4>(h, p);
-        if (bin == 6) r = launch_dense_r<32, 8>(h, p);
-        if (bin == 7) r = launch_dense_r<32, 16>(h, p);
+        if (bin == 0) {
+            r = launch_dense_r<8, 1, true>(h, p);
+            if (r == -100) r = launch_dense_r<16, 1, true>(h, p);
+            if (r == -100) r = launch_dense_r<32, 1, true>(h, p);
+        } else if (bin == 1) {
+            r = launch_dense_r<16, 1, false>(h, p);
+            if (r == -100) r = launch_dense_r<32, 1, false>(h, p);
+        } else if (bin == 2) r = launch_dense_r<32, 1, false>(h, p);
+        else if (bin == 3) r = launch_dense_r<32, 2, false>(h, p);
+        else if (bin == 4) r = launch_dense_r<32, 4, false>(h, p);
+        else if (bin == 5) r = launch_dense_r<32, 8, false>(h, p);
+        else r = launch_dense_r<32, 16, false>(h, p);
         if (r == -100) return fail(GIBBS_E_ARG, "gibbs_sweep: n_wk row segment too long for the shared-memory ring (K > ~28000)");
         TRY(r);
     }
@@ -509,7 +582,7 @@ extern "C" int gibbs_get_state(gibbs_t *h, int32_t *z, int32_t *n_wk, int32_t *n
         TRY(reserve(h, h->scratch, (size_t)h->N * sizeof(int)));
         int *t_z = reinterpret_cast<int *>(h->scratch.p);
         const long long blocks = (D * 32 + 255) / 256;
-        export_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr.p, h->lab_ptr.p, h->lab_idx.p, h->rec.p, t_z);
+        export_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->work.p, h->doc_ptr.p, h->lab_idx.p, h->rec.p, t_z);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(z, t_z, sizeof(int) * h->N, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -532,7 +605,7 @@ extern "C" int gibbs_set_z(gibbs_t *h, const int32_t *z) {
     CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
     if (D > 0) {
         const long long blocks = (D * 32 + 255) / 256;
-        set_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->doc_ptr.p, h->lab_ptr.p, h->lab_idx.p, t_z, h->rec.p, h->err_flag.p);
+        set_z_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->work.p, h->doc_ptr.p, h->lab_idx.p, t_z, h->rec.p, h->err_flag.p);
         CK(cudaGetLastError());
     }
     int err = 0;
@@ -574,9 +647,7 @@ extern "C" int gibbs_emit_phi(gibbs_t *h, double *phi_KV, int32_t smoothed) {
     if (!smoothed) {
         // CascadeLDA.py:394-395 / HSLDA.py:151-152 divide by the row sums of n_k_v itself (they differ from n_zk when
         // the table carries SubLDA's spurious initial counts), so sum the table's columns here
-        CK(cudaMemsetAsync(h->colsum.p, 0, sizeof(int) * h->ldk, h->stream));
-        column_sums_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->n_wk.p, h->colsum.p, V, h->ldk);
-        CK(cudaGetLastError());
+        TRY(column_sums(h, h->colsum.p));
         den = h->colsum.p;
     }
     dim3 grid((V + 31) / 32, (K + 31) / 32), block(32, 8);

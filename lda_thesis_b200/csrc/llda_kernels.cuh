@@ -7,31 +7,45 @@
 
 // ----------------------------------------------------------------------------------------------
 // Draw record: 8 bytes per draw.  x = word id, y = (f << 16) | j  where j is the index of the
-// draw's current topic inside its document's label list (z = lab_idx[lab_ptr[d] + j]).
+// draw's current topic inside its document's label list (z = lab_idx[lab0 + j]).
 // ----------------------------------------------------------------------------------------------
 #define REC_F(y)  ((int)((unsigned)(y) >> 16))
 #define REC_J(y)  ((int)((unsigned)(y) & 0xffffu))
 #define REC_PACK(f, j) ((int)(((unsigned)(f) << 16) | (unsigned)(j)))
 
+// Label lists of at most GIBBS_SERIAL_MAX topics add their weights left to right (one thread can own the
+// document); longer lists add them in 32-lane Kogge-Stone chunks.  Same constant as ORACLE_SERIAL_MAX.
+#define GIBBS_SERIAL_MAX 8
+
+// One document as the sampling kernels see it (32 bytes, one per work-list entry).
+// Record i of the document is R[rbase + i * stride]: stride 1 for group-per-document kernels, stride 32 for the
+// thread-per-document kernel (32 documents of a warp interleaved, so a warp reads one 256-byte line per step).
+struct __align__(16) DocDesc {
+    long long rbase;
+    long long lab0;     // first entry of the label list in lab_idx / n_dk_act
+    int len;            // draws
+    int A;              // label-list length
+    int stride;
+    int doc;            // document id inside the shard
+};
+
 struct SweepParams {
-    const long long *doc_ptr;     // [D+1]
-    const long long *lab_ptr;     // [D+1]
-    const int       *lab_idx;     // [lab_ptr[D]]
-    int             *n_dk_act;    // [lab_ptr[D]]
-    int2            *rec;         // [N]
+    const DocDesc   *work;        // work list of this launch
+    long long        n_work;
+    const int       *lab_idx;     // [n_lab]
+    int             *n_dk_act;    // [n_lab]
+    int2            *R;           // draw records
     const int       *n_wk;        // [V][ldk] frozen for the refresh block
     int             *delta_wk;    // [V][ldk] +-f land here
     const int       *n_k;         // [K] frozen
     const int       *seg;         // [2*D] or nullptr
-    const int       *doc_list;    // documents of this launch
-    long long        n_list;
     unsigned long long *counter;  // work counter (zeroed before launch)
     unsigned long long *changed;  // draws whose topic changed
     int              ldk;
     int              row_ints;    // ints per ring slot (max segment length, multiple of 4)
     float            alpha, beta, vbeta;
     unsigned         seed_lo, seed_hi, sweep;
-    long long        draw_base;
+    long long        doc_base;    // global id of the shard's document 0 (RNG addressing)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -46,18 +60,177 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Weight of one active topic, one IEEE operation per statement (mirrored by oracle/gibbs_oracle.c:snapshot_doc):
+//   (n_dk + alpha) * (n_wk + beta) / (n_k + V*beta)   with the draw's own f removed from all three counts.
+__device__ __forceinline__ float topic_weight(int nd, int nw, int nk, float alpha, float beta, float vbeta) {
+    const float a = __fadd_rn((float)nd, alpha);
+    const float b = __fadd_rn((float)nw, beta);
+    const float cc = __fadd_rn((float)nk, vbeta);
+    return __fdiv_rn(__fmul_rn(a, b), cc);
+}
+
 // ----------------------------------------------------------------------------------------------
-// Snapshot sweep.  A group of G lanes owns one document at a time; lane gl (+32*c for chunk c when
-// G == 32) owns one entry of the document's label list.  Per draw:
+// Snapshot sweep, thread-per-document (label lists of at most GIBBS_SERIAL_MAX topics).
+//
+// A warp takes a slice of 32 documents (sorted by label-list length, then by length, so the lanes of a slice
+// are alike); lane l owns document l for its whole length and keeps the label ids, n_dk and the n_k snapshot of
+// its <= AMAX topics in registers.  The records of the 32 documents are interleaved (stride 32), so each step
+// is ONE coalesced 256-byte record load per warp; the counts n_wk[v][label] are 4-byte gathers issued two
+// steps ahead into registers (they touch |label list| 32-byte sectors of the row, not the whole row).  No
+// shuffles, scans or ballots: the weights are added left to right by the owning thread, one Philox block
+// serves four consecutive steps of all 32 lanes.  +-f go to the delta table with RED.ADD.
+// ----------------------------------------------------------------------------------------------
+template <int AMAX>
+__device__ __forceinline__ void lane_slice(const SweepParams &p, const DocDesc dd, const int steps, unsigned &n_changed) {
+    const float alpha = p.alpha, beta = p.beta, vbeta = p.vbeta;
+    const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
+    const int ldk = p.ldk;
+    const int *__restrict__ n_wk = p.n_wk;
+    const int A = dd.A, len = dd.len;
+    const unsigned docg = (unsigned)(p.doc_base + dd.doc);
+
+    int lab[AMAX], ndk[AMAX], nkb[AMAX];
+#pragma unroll
+    for (int j = 0; j < AMAX; ++j) {
+        lab[j] = 0; ndk[j] = 0;
+        if (j < A) { lab[j] = p.lab_idx[dd.lab0 + j]; ndk[j] = p.n_dk_act[dd.lab0 + j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < AMAX; ++j) nkb[j] = (j < A) ? p.n_k[lab[j]] - ndk[j] : 0;
+
+    int2 *rp = p.R + dd.rbase;                       // record i at rp[i * 32]
+    int2 c[4], nx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        c[q] = (q < len) ? rp[(size_t)q * 32] : make_int2(0, 0);
+        nx[q] = (4 + q < len) ? rp[(size_t)(4 + q) * 32] : make_int2(0, 0);
+    }
+    int g[2][AMAX];                                  // counts of steps s (even slot) and s + 1 (odd slot)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < AMAX; ++j)
+            g[q][j] = (j < A && q < len) ? __ldg(n_wk + (size_t)c[q].x * ldk + lab[j]) : 0;
+
+    for (int s0 = 0; s0 < steps; s0 += 4) {
+        const uint4 rw = philox_block((unsigned)(s0 >> 2), docg, p.sweep, GIBBS_STREAM_SWEEP, key);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int s = s0 + q;
+            const bool live = s < len;
+            const int v = c[q].x, y = c[q].y;
+            const int f = REC_F(y), jo = REC_J(y);
+            int nw[AMAX];
+#pragma unroll
+            for (int j = 0; j < AMAX; ++j) nw[j] = g[q & 1][j];
+            {   // counts of step s + 2
+                const int v2 = (q < 2) ? c[q + 2].x : nx[q - 2].x;
+                const bool live2 = s + 2 < len;
+#pragma unroll
+                for (int j = 0; j < AMAX; ++j)
+                    g[q & 1][j] = (j < A && live2) ? __ldg(n_wk + (size_t)v2 * ldk + lab[j]) : 0;
+            }
+            float cum[AMAX];
+            float run = 0.0f;
+#pragma unroll
+            for (int j = 0; j < AMAX; ++j) {
+                const int self = (j == jo) ? f : 0;
+                const int nd = ndk[j] - self;
+                const float w = (j < A) ? topic_weight(nd, nw[j] - self, nkb[j] + nd, alpha, beta, vbeta) : 0.0f;
+                run = __fadd_rn(run, w);
+                cum[j] = run;
+            }
+            const unsigned xw = (q == 0) ? rw.x : (q == 1) ? rw.y : (q == 2) ? rw.z : rw.w;
+            const float thr = __fmul_rn(u01_f32(xw), run);
+            int jn = A - 1;
+#pragma unroll
+            for (int j = AMAX - 1; j >= 0; --j)
+                if (cum[j] > thr) jn = j;            // smallest j with cum[j] > thr (entries past A-1 repeat the total)
+            if (live && jn != jo) {
+                int lo = 0, ln = 0;
+#pragma unroll
+                for (int j = 0; j < AMAX; ++j) {
+                    if (j == jo) { ndk[j] -= f; lo = lab[j]; }
+                    if (j == jn) { ndk[j] += f; ln = lab[j]; }
+                }
+                int *drow = p.delta_wk + (size_t)v * ldk;
+                atomicAdd(drow + lo, -f);
+                atomicAdd(drow + ln, f);
+                rp[(size_t)s * 32].y = REC_PACK(f, jn);
+                ++n_changed;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            c[q] = nx[q];
+            nx[q] = (s0 + 8 + q < len) ? rp[(size_t)(s0 + 8 + q) * 32] : make_int2(0, 0);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < AMAX; ++j)
+        if (j < A) p.n_dk_act[dd.lab0 + j] = ndk[j];
+}
+
+__global__ void __launch_bounds__(128) llda_lane_kernel(const SweepParams p) {
+    const int lane = threadIdx.x & 31;
+    unsigned n_changed = 0;
+    while (true) {
+        unsigned long long sl = 0;
+        if (lane == 0) sl = atomicAdd(p.counter, 1ull);
+        sl = __shfl_sync(0xffffffffu, sl, 0);
+        const long long idx = (long long)sl * 32 + lane;
+        if ((long long)sl * 32 >= p.n_work) break;
+        DocDesc dd;
+        dd.rbase = 0; dd.lab0 = 0; dd.len = 0; dd.A = 0; dd.stride = 32; dd.doc = 0;
+        if (idx < p.n_work) dd = p.work[idx];
+        const int amax = __reduce_max_sync(0xffffffffu, dd.A);
+        const int steps = __reduce_max_sync(0xffffffffu, dd.len);
+        if (amax <= 2) lane_slice<2>(p, dd, steps, n_changed);
+        else if (amax <= 4) lane_slice<4>(p, dd, steps, n_changed);
+        else if (amax <= 6) lane_slice<6>(p, dd, steps, n_changed);
+        else lane_slice<8>(p, dd, steps, n_changed);
+    }
+    n_changed = __reduce_add_sync(0xffffffffu, n_changed);
+    if (lane == 0 && n_changed) atomicAdd(p.changed, (unsigned long long)n_changed);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Inclusive prefix sum of x over the G lanes of a group.
+//   SERIAL: left to right (x0, x0+x1, (x0+x1)+x2, ...) over the first GIBBS_SERIAL_MAX lanes -- the order of the
+//           thread-per-document kernel, so both kernels give the same bits for short label lists;
+//   else  : Kogge-Stone (offsets 1, 2, 4, ...), whose first G lanes equal those of the 32-lane scan.
+// ----------------------------------------------------------------------------------------------
+template <int G, bool SERIAL>
+__device__ __forceinline__ float group_scan(float x, const int gl, const unsigned gmask) {
+    if constexpr (SERIAL) {
+        float cum = x;
+#pragma unroll
+        for (int j = 1; j < GIBBS_SERIAL_MAX; ++j) {
+            const float t = __shfl_sync(gmask, cum, j - 1, G);
+            if (gl == j) cum = __fadd_rn(t, x);
+        }
+        return cum;
+    } else {
+#pragma unroll
+        for (int off = 1; off < G; off <<= 1) {
+            const float y = __shfl_up_sync(gmask, x, off, G);
+            if (gl >= off) x = __fadd_rn(x, y);
+        }
+        return x;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Snapshot sweep, dense row fetch.  A group of G lanes owns one document at a time; lane gl (+32*c for chunk c
+// when G == 32) owns one entry of the document's label list.  Per draw:
 //   cp.async the draw's n_wk row (segment) into a shared-memory ring R-1 draws ahead,
-//   gather the active entries from shared memory, weight = (n_dk+alpha)*(n_wk+beta)/(n_k+V*beta) with the
-//   draw's own f removed, Kogge-Stone prefix sum over the group, Philox uniform, first cum > u*total,
-//   +-f to the delta table with RED, n_dk stays in registers until the document ends.
-// Arithmetic is restated operation for operation by oracle/gibbs_oracle.c:snapshot_doc.
+//   gather the active entries from shared memory, weight as above, prefix sum over the group, Philox uniform,
+//   first cum > u*total, +-f to the delta table with RED, n_dk stays in registers until the document ends.
 // ----------------------------------------------------------------------------------------------
-template <int G, int NCH, int R>
-__global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p) {
+template <int G, int NCH, int R, bool SERIAL>
+__global__ void __launch_bounds__(256) llda_dense_kernel(const SweepParams p) {
     static_assert(G == 32 || NCH == 1, "multi-chunk label lists need a full warp");
+    static_assert(!SERIAL || (NCH == 1 && G >= GIBBS_SERIAL_MAX), "serial sums are for short label lists");
     static_assert((R & (R - 1)) == 0 && R >= 2, "ring depth must be a power of two");
     constexpr int P = 2 * R - 1;   // record prefetch distance
     constexpr int M = 2 * R;       // record ring slots
@@ -80,13 +253,15 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
     const int ldk = p.ldk;
 
     // group state
-    long long n = 0, n_end = 0, lab0 = 0;
-    int A = 0, i = 0, seg_lo = 0, seg_n16 = 0;
+    DocDesc dd;
+    dd.rbase = 0; dd.lab0 = 0; dd.len = 0; dd.A = 0; dd.stride = 1; dd.doc = 0;
+    int i = 0, seg_lo = 0, seg_n16 = 0;
+    unsigned docg = 0;
     int lab[NCH], ndk[NCH], nkb[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { lab[c] = 0; ndk[c] = 0; nkb[c] = 0; }
     uint4 rw = make_uint4(0, 0, 0, 0);
-    long long rB0 = -(1ll << 40);
+    int rB0 = -(1 << 30);
     bool have = false, done = false;
     unsigned n_changed = 0;
 
@@ -95,42 +270,41 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
         int *dst = ring + (size_t)slot * row_ints;
         for (int c16 = gl; c16 < seg_n16; c16 += G) cp_async16(dst + c16 * 4, src + c16 * 4);
     };
+    auto rec_at = [&](int q) { return p.R + dd.rbase + (long long)q * dd.stride; };
 
     while (true) {
         if (!have && !done) {
             unsigned long long di = 0;
             if (gl == 0) di = atomicAdd(p.counter, 1ull);
             di = __shfl_sync(gmask, di, gbase);
-            if (di >= (unsigned long long)p.n_list) {
+            if (di >= (unsigned long long)p.n_work) {
                 done = true;
             } else {
-                const int d = p.doc_list[di];
-                n = p.doc_ptr[d];
-                n_end = p.doc_ptr[d + 1];
-                lab0 = p.lab_ptr[d];
-                A = (int)(p.lab_ptr[d + 1] - lab0);
-                if (p.seg) { seg_lo = p.seg[2 * d]; seg_n16 = (p.seg[2 * d + 1] - seg_lo) >> 2; }
+                dd = p.work[di];
+                docg = (unsigned)(p.doc_base + dd.doc);
+                if (p.seg) { seg_lo = p.seg[2 * dd.doc]; seg_n16 = (p.seg[2 * dd.doc + 1] - seg_lo) >> 2; }
                 else       { seg_lo = 0; seg_n16 = ldk >> 2; }
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const int j = c * G + gl;
-                    if (j < A) {
-                        lab[c] = p.lab_idx[lab0 + j];
-                        ndk[c] = p.n_dk_act[lab0 + j];
+                    if (j < dd.A) {
+                        lab[c] = p.lab_idx[dd.lab0 + j];
+                        ndk[c] = p.n_dk_act[dd.lab0 + j];
                         nkb[c] = p.n_k[lab[c]] - ndk[c];
                     } else { lab[c] = seg_lo; ndk[c] = 0; nkb[c] = 0; }
                 }
-                if (n < n_end) {
+                if (dd.len > 0) {
                     have = true;
                     i = 0;
+                    rB0 = -(1 << 30);
                     for (int q = gl; q < P; q += G)
-                        if (n + q < n_end) cp_async8(&meta[q & (M - 1)], &p.rec[n + q]);
+                        if (q < dd.len) cp_async8(&meta[q & (M - 1)], rec_at(q));
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncwarp(gmask);
 #pragma unroll
                     for (int r = 0; r < R - 1; ++r) {
-                        if (n + r < n_end) issue_row(r, meta[r].x);
+                        if (r < dd.len) issue_row(r, meta[r].x);
                         cp_async_commit();
                     }
                 }
@@ -138,9 +312,10 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (have) {
-            // -- prefetch: record of draw n+P, row of draw n+R-1
-            if (gl == 0 && n + P < n_end) cp_async8(&meta[(i + P) & (M - 1)], &p.rec[n + P]);
-            if (n + (R - 1) < n_end) issue_row((i + R - 1) & (R - 1), meta[(i + R - 1) & (M - 1)].x);
+            const int A = dd.A;
+            // -- prefetch: record of draw i+P, row of draw i+R-1
+            if (gl == 0 && i + P < dd.len) cp_async8(&meta[(i + P) & (M - 1)], rec_at(i + P));
+            if (i + (R - 1) < dd.len) issue_row((i + R - 1) & (R - 1), meta[(i + R - 1) & (M - 1)].x);
             cp_async_commit();
             cp_async_wait<R - 1>();
             __syncwarp(gmask);
@@ -159,17 +334,9 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
                 if (j < A) {
                     const int self = (j == jo) ? f : 0;
                     const int nd = ndk[c] - self;
-                    const int nw = row[lab[c]] - self;
-                    const float a = __fadd_rn((float)nd, alpha);
-                    const float b = __fadd_rn((float)nw, beta);
-                    const float cc = __fadd_rn((float)(nkb[c] + nd), vbeta);
-                    x = __fdiv_rn(__fmul_rn(a, b), cc);
+                    x = topic_weight(nd, row[lab[c]] - self, nkb[c] + nd, alpha, beta, vbeta);
                 }
-#pragma unroll
-                for (int off = 1; off < G; off <<= 1) {
-                    const float y = __shfl_up_sync(gmask, x, off, G);
-                    if (gl >= off) x = __fadd_rn(x, y);
-                }
+                x = group_scan<G, SERIAL>(x, gl, gmask);
                 cum[c] = __fadd_rn(carry, x);
                 carry = __fadd_rn(carry, __shfl_sync(gmask, x, G - 1, G));
             }
@@ -179,15 +346,14 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
             for (int c = 1; c < NCH; ++c) if (((A - 1) / G) == c) cl = cum[c];
             const float total = __shfl_sync(gmask, cl, (A - 1) & (G - 1), G);
 
-            // -- uniform
-            const long long t = p.draw_base + n;
-            const long long blk = t >> 2;
+            // -- uniform: lane gl of the group holds the Philox block of positions 4*(rB0+gl) ..
+            const int blk = i >> 2;
             if (blk < rB0 || blk >= rB0 + G) {
                 rB0 = blk;
-                rw = philox_block((uint64_t)(blk + gl), p.sweep, GIBBS_STREAM_SWEEP, key);
+                rw = philox_block((unsigned)(blk + gl), docg, p.sweep, GIBBS_STREAM_SWEEP, key);
             }
-            const unsigned mine = select_word(rw, (unsigned)(t & 3));
-            const unsigned xw = __shfl_sync(gmask, mine, (int)(blk - rB0), G);
+            const unsigned mine = select_word(rw, (unsigned)(i & 3));
+            const unsigned xw = __shfl_sync(gmask, mine, blk - rB0, G);
             const float thr = __fmul_rn(u01_f32(xw), total);
 
             // -- first index with cum > thr, else A-1
@@ -208,14 +374,14 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
                     if (j == jo) { ndk[c] -= f; atomicAdd(&p.delta_wk[(size_t)v * ldk + lab[c]], -f); }
                     else if (j == jn) { ndk[c] += f; atomicAdd(&p.delta_wk[(size_t)v * ldk + lab[c]], f); }
                 }
-                if (gl == 0) { p.rec[n].y = REC_PACK(f, jn); ++n_changed; }
+                if (gl == 0) { rec_at(i)->y = REC_PACK(f, jn); ++n_changed; }
             }
-            ++n; ++i;
-            if (n == n_end) {
+            ++i;
+            if (i == dd.len) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const int j = c * G + gl;
-                    if (j < A) p.n_dk_act[lab0 + j] = ndk[c];
+                    if (j < A) p.n_dk_act[dd.lab0 + j] = ndk[c];
                 }
                 have = false;
             }
@@ -225,23 +391,17 @@ __global__ void __launch_bounds__(256) llda_snapshot_kernel(const SweepParams p)
 }
 
 // ----------------------------------------------------------------------------------------------
-// Snapshot sweep, masked-gather row fetch (label lists of at most G <= 32 topics).
+// Snapshot sweep, masked-gather row fetch for label lists of 9..32 topics (G = 16 or 32 lanes per document).
 //
-// A group of G lanes owns one document; lane j owns entry j of its label list and keeps n_dk[j] in a
-// register for the whole document.  The document is walked in chunks of G draws:
-//   * lane i of the group holds the record of draw n0+i (one coalesced 8-byte load per lane per chunk,
-//     the next chunk's records are requested one chunk ahead) and computes that draw's Philox word;
-//   * per draw, lane j needs ONE count, n_wk[v][lab_j]: a 4-byte load that touches |label list| 32-byte
-//     sectors of the row instead of the whole ldk-wide row.  The loads run R draws ahead in a register
-//     ring, so R x (warps per SM) independent sectors are in flight per lane;
-//   * weight, Kogge-Stone scan, threshold, ballot exactly as in the dense-row kernel -- the arithmetic
-//     (and therefore the oracle restatement, oracle/gibbs_oracle.c:snapshot_doc) is the same;
-//   * +-f go to the delta table with RED.ADD; changed records are written back once per chunk.
-// No shared memory, no barriers: occupancy is bounded by registers only.
+// Lane j owns entry j of the label list and keeps n_dk[j] in a register.  The document is walked in chunks of G
+// draws: lane i of the group holds the record of draw n0+i (one coalesced 8-byte load per lane per chunk, the
+// next chunk's records are requested one chunk ahead) and computes that draw's Philox word; per draw, lane j
+// needs ONE count, n_wk[v][lab_j] -- a 4-byte load running R draws ahead in a register ring.  Same arithmetic
+// as the dense kernel (Kogge-Stone sums), no shared memory.
 // ----------------------------------------------------------------------------------------------
 template <int G, int R>
 __global__ void __launch_bounds__(256, 3) llda_gather_kernel(const SweepParams p) {
-    static_assert(G >= 4 && G <= 32 && (G & (G - 1)) == 0, "group width");
+    static_assert(G >= 16 && G <= 32 && (G & (G - 1)) == 0, "group width");
     static_assert(R >= 1 && R <= G && (G % R) == 0, "ring depth must divide the chunk");
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
@@ -258,39 +418,40 @@ __global__ void __launch_bounds__(256, 3) llda_gather_kernel(const SweepParams p
         unsigned long long di = 0;
         if (gl == 0) di = atomicAdd(p.counter, 1ull);
         di = __shfl_sync(gmask, di, 0, G);
-        if (di >= (unsigned long long)p.n_list) break;
-        const int d = p.doc_list[di];
-        long long n0 = p.doc_ptr[d];
-        const long long n_end = p.doc_ptr[d + 1];
-        const long long lab0 = p.lab_ptr[d];
-        const int A = (int)(p.lab_ptr[d + 1] - lab0);
-        if (n0 >= n_end) continue;
+        if (di >= (unsigned long long)p.n_work) break;
+        const DocDesc dd = p.work[di];
+        const int A = dd.A, len = dd.len;
+        if (len <= 0) continue;
+        const unsigned docg = (unsigned)(p.doc_base + dd.doc);
+        int2 *rp = p.R + dd.rbase;
+        const long long st = dd.stride;
         int lab = 0, ndk = 0, nkb = 0;
         if (gl < A) {
-            lab = p.lab_idx[lab0 + gl];
-            ndk = p.n_dk_act[lab0 + gl];
+            lab = p.lab_idx[dd.lab0 + gl];
+            ndk = p.n_dk_act[dd.lab0 + gl];
             nkb = p.n_k[lab] - ndk;
         }
+        int n0 = 0;
         int2 cur = make_int2(0, 0), nxt = make_int2(0, 0);
-        if (n0 + gl < n_end) cur = p.rec[n0 + gl];
-        if (n0 + G + gl < n_end) nxt = p.rec[n0 + G + gl];
+        if (gl < len) cur = rp[gl * st];
+        if (G + gl < len) nxt = rp[(G + gl) * st];
         int nwq[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int v = __shfl_sync(gmask, cur.x, r, G);
-            nwq[r] = (gl < A && n0 + r < n_end) ? __ldg(n_wk + (size_t)v * ldk + lab) : 0;
+            nwq[r] = (gl < A && r < len) ? __ldg(n_wk + (size_t)v * ldk + lab) : 0;
         }
 
         // ---- chunks of G draws
         while (true) {
-            const unsigned word = philox_word((uint64_t)(p.draw_base + n0 + gl), p.sweep, GIBBS_STREAM_SWEEP, key);
+            const unsigned word = philox_word(docg, (unsigned)(n0 + gl), p.sweep, GIBBS_STREAM_SWEEP, key);
             int newy = cur.y;
             for (int i0 = 0; i0 < G; i0 += R) {
-                if (n0 + i0 >= n_end) break;
+                if (n0 + i0 >= len) break;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int i = i0 + r;
-                    const bool live = n0 + i < n_end;
+                    const bool live = n0 + i < len;
                     const int v = __shfl_sync(gmask, cur.x, i, G);
                     const int y = __shfl_sync(gmask, cur.y, i, G);
                     const unsigned xw = __shfl_sync(gmask, word, i, G);
@@ -300,42 +461,36 @@ __global__ void __launch_bounds__(256, 3) llda_gather_kernel(const SweepParams p
                         const int ii = i + R;
                         const int srcx = (ii < G) ? cur.x : nxt.x;
                         const int v2 = __shfl_sync(gmask, srcx, ii & (G - 1), G);
-                        nwq[r] = (gl < A && n0 + ii < n_end) ? __ldg(n_wk + (size_t)v2 * ldk + lab) : 0;
+                        nwq[r] = (gl < A && n0 + ii < len) ? __ldg(n_wk + (size_t)v2 * ldk + lab) : 0;
                     }
                     float x = 0.0f;
                     const int self = (gl == jo) ? f : 0;
                     const int nd = ndk - self;
-                    if (gl < A) {
-                        const float a = __fadd_rn((float)nd, alpha);
-                        const float b = __fadd_rn((float)(nw_raw - self), beta);
-                        const float cc = __fadd_rn((float)(nkb + nd), vbeta);
-                        x = __fdiv_rn(__fmul_rn(a, b), cc);
-                    }
-#pragma unroll
-                    for (int off = 1; off < G; off <<= 1) {
-                        const float t = __shfl_up_sync(gmask, x, off, G);
-                        if (gl >= off) x = __fadd_rn(x, t);
-                    }
+                    if (gl < A) x = topic_weight(nd, nw_raw - self, nkb + nd, alpha, beta, vbeta);
+                    x = group_scan<G, false>(x, gl, gmask);
                     const float total = __shfl_sync(gmask, x, A - 1, G);
                     const float thr = __fmul_rn(u01_f32(xw), total);
                     unsigned bal = __ballot_sync(gmask, (gl < A) && (x > thr));
                     bal = (bal >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
                     const int jn = bal ? (__ffs(bal) - 1) : (A - 1);
                     if (live && jn != jo) {
-                        if (gl == jo) { ndk -= f; atomicAdd(&p.delta_wk[(size_t)v * ldk + lab], -f); }
-                        else if (gl == jn) { ndk += f; atomicAdd(&p.delta_wk[(size_t)v * ldk + lab], f); }
+                        if (gl == jo || gl == jn) {
+                            const int df = (gl == jo) ? -f : f;
+                            ndk += df;
+                            atomicAdd(&p.delta_wk[(size_t)v * ldk + lab], df);
+                        }
                         if (gl == i) { newy = REC_PACK(f, jn); ++n_changed; }
                     }
                 }
             }
-            if (newy != cur.y) p.rec[n0 + gl].y = newy;
+            if (newy != cur.y) rp[(n0 + gl) * st].y = newy;
             n0 += G;
-            if (n0 >= n_end) break;
+            if (n0 >= len) break;
             cur = nxt;
             nxt = make_int2(0, 0);
-            if (n0 + G + gl < n_end) nxt = p.rec[n0 + G + gl];
+            if (n0 + G + gl < len) nxt = rp[(n0 + G + gl) * st];
         }
-        if (gl < A) p.n_dk_act[lab0 + gl] = ndk;
+        if (gl < A) p.n_dk_act[dd.lab0 + gl] = ndk;
     }
     n_changed = __reduce_add_sync(0xffffffffu, n_changed);
     if (lane == 0 && n_changed) atomicAdd(p.changed, (unsigned long long)n_changed);
@@ -344,19 +499,20 @@ __global__ void __launch_bounds__(256, 3) llda_gather_kernel(const SweepParams p
 // ----------------------------------------------------------------------------------------------
 // Exact sweep: one warp walks the corpus in order with live counts in fp64, the operation order of
 // LabeledLDA.py:109-125 (restated by oracle/gibbs_oracle.c:oracle_llda_exact_sweep).
+// desc[d] is indexed by document id (corpus order).
 // ----------------------------------------------------------------------------------------------
 struct ExactParams {
-    const long long *doc_ptr, *lab_ptr;
+    const DocDesc *desc;
     const int *lab_idx;
     int *n_dk_act;
-    int2 *rec;
+    int2 *R;
     int *n_wk;
     int *n_k;
     long long d_begin, d_end;
     int ldk;
     double alpha, beta, vbeta;
     unsigned seed_lo, seed_hi, sweep;
-    long long draw_base;
+    long long doc_base;
     unsigned long long *changed;
 };
 
@@ -368,11 +524,13 @@ __global__ void __launch_bounds__(32) llda_exact_kernel(const ExactParams p) {
     const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
     unsigned long long n_changed = 0;
     for (long long d = p.d_begin; d < p.d_end; ++d) {
-        const long long lab0 = p.lab_ptr[d];
-        const int A = (int)(p.lab_ptr[d + 1] - lab0);
+        const DocDesc dd = p.desc[d];
+        const long long lab0 = dd.lab0;
+        const int A = dd.A;
         const int nch = (A + 31) >> 5;
-        for (long long n = p.doc_ptr[d]; n < p.doc_ptr[d + 1]; ++n) {
-            const int2 mt = p.rec[n];
+        for (int i = 0; i < dd.len; ++i) {
+            int2 *rec = p.R + dd.rbase + (long long)i * dd.stride;
+            const int2 mt = *rec;
             const int v = mt.x, f = REC_F(mt.y), jo = REC_J(mt.y);
             const int zo = p.lab_idx[lab0 + jo];
             if (lane == 0) {
@@ -381,7 +539,7 @@ __global__ void __launch_bounds__(32) llda_exact_kernel(const ExactParams p) {
                 nk[zo] -= f;                        // :111
             }
             __syncwarp();
-            const uint32_t xw = philox_word((uint64_t)(p.draw_base + n), p.sweep, GIBBS_STREAM_SWEEP, key);
+            const uint32_t xw = philox_word((unsigned)(p.doc_base + d), (unsigned)i, p.sweep, GIBBS_STREAM_SWEEP, key);
             const double u = u01_f64(xw);
             // pass 1: total; pass 2: pick.  Both passes run the same serial sum, so cum values are identical.
             double run = 0.0;
@@ -423,7 +581,7 @@ __global__ void __launch_bounds__(32) llda_exact_kernel(const ExactParams p) {
             }
             const int zn = p.lab_idx[lab0 + jn];
             if (lane == 0) {
-                if (jn != jo) { p.rec[n].y = REC_PACK(f, jn); ++n_changed; }   // :121
+                if (jn != jo) { rec->y = REC_PACK(f, jn); ++n_changed; }   // :121
                 nwk[(size_t)v * p.ldk + zn] += f;    // :123
                 ndk[lab0 + jn] += f;                 // :124
                 nk[zn] += f;                         // :125
@@ -435,51 +593,50 @@ __global__ void __launch_bounds__(32) llda_exact_kernel(const ExactParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Corpus preparation, histogram, merge, export.
+// Corpus preparation, histogram, merge, export.  One warp per work-list entry (= per document); the CSR side
+// (word / freq / z in corpus order) is indexed through doc_ptr[dd.doc], the record side through (rbase, stride).
 // ----------------------------------------------------------------------------------------------
 
-// One warp per document: pack records; z from z_init (global topic ids -> label-list index) or
-// Uniform(label list) from Philox stream 1.  err[0] is set when a z_init value is not in the list.
-__global__ void prepare_records_kernel(long long D, const long long *doc_ptr, const int *word, const int *freq,
-                                       const int *z_init, const long long *lab_ptr, const int *lab_idx,
-                                       int2 *rec, int V, uint2 key, long long draw_base, int *err) {
-    const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Pack records; z from z_init (global topic ids -> label-list index) or Uniform(label list) from Philox stream 1.
+// err[0] is set when a z_init value is not in the list.
+__global__ void prepare_records_kernel(long long n_work, const DocDesc *work, const long long *doc_ptr, const int *word,
+                                       const int *freq, const int *z_init, const int *lab_idx, int2 *R, int V, uint2 key,
+                                       long long doc_base, int *err) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (d >= D) return;
-    const long long lab0 = lab_ptr[d];
-    const int A = (int)(lab_ptr[d + 1] - lab0);
-    for (long long n = doc_ptr[d] + lane; n < doc_ptr[d + 1]; n += 32) {
-        const int f = freq ? freq[n] : 1;
+    if (w >= n_work) return;
+    const DocDesc dd = work[w];
+    const long long src = doc_ptr[dd.doc];
+    for (int i = lane; i < dd.len; i += 32) {
+        const int f = freq ? freq[src + i] : 1;
         int j = -1;
         if (z_init) {
-            const int zg = z_init[n];
-            for (int q = 0; q < A; ++q)
-                if (lab_idx[lab0 + q] == zg) { j = q; break; }
-        } else if (A > 0) {
-            const uint32_t w = philox_word((uint64_t)(draw_base + n), 0u, GIBBS_STREAM_INIT, key);
-            j = (int)(((uint64_t)w * (uint64_t)A) >> 32);
+            const int zg = z_init[src + i];
+            for (int q = 0; q < dd.A; ++q)
+                if (lab_idx[dd.lab0 + q] == zg) { j = q; break; }
+        } else if (dd.A > 0) {
+            const uint32_t x = philox_word((unsigned)(doc_base + dd.doc), (unsigned)i, 0u, GIBBS_STREAM_INIT, key);
+            j = (int)(((uint64_t)x * (uint64_t)dd.A) >> 32);
         }
-        int v = word[n];
+        int v = word[src + i];
         if (j < 0 || f < 0 || f > 0xffff || v < 0 || v >= V) { atomicExch(err, 1); j = 0; v = 0; }
-        rec[n] = make_int2(v, REC_PACK(f, j));
+        R[dd.rbase + (long long)i * dd.stride] = make_int2(v, REC_PACK(f, j));
     }
 }
 
-// One warp per document: histogram (LabeledLDA.py:89-92).
-__global__ void counts_build_kernel(long long D, const long long *doc_ptr, const long long *lab_ptr,
-                                    const int *lab_idx, const int2 *rec, int ldk,
-                                    int *n_wk, int *n_dk_act, int *n_k) {
-    const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Histogram (LabeledLDA.py:89-92).  n_k is NOT touched here: it is the column sum of n_wk (column_sums_kernel).
+__global__ void counts_build_kernel(long long n_work, const DocDesc *work, const int *lab_idx, const int2 *R, int ldk,
+                                    int *n_wk, int *n_dk_act) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (d >= D) return;
-    const long long lab0 = lab_ptr[d];
-    for (long long n = doc_ptr[d] + lane; n < doc_ptr[d + 1]; n += 32) {
-        const int2 r = rec[n];
+    if (w >= n_work) return;
+    const DocDesc dd = work[w];
+    for (int i = lane; i < dd.len; i += 32) {
+        const int2 r = R[dd.rbase + (long long)i * dd.stride];
         const int f = REC_F(r.y), j = REC_J(r.y);
-        const int k = lab_idx[lab0 + j];
+        const int k = lab_idx[dd.lab0 + j];
         atomicAdd(&n_wk[(size_t)r.x * ldk + k], f);
-        atomicAdd(&n_dk_act[lab0 + j], f);
-        atomicAdd(&n_k[k], f);
+        atomicAdd(&n_dk_act[dd.lab0 + j], f);
     }
 }
 
@@ -490,30 +647,32 @@ __global__ void add_counts_kernel(long long n, const int *word, const int *topic
 }
 
 // Replace z: global topic ids -> label-list index inside the existing records.
-__global__ void set_z_kernel(long long D, const long long *doc_ptr, const long long *lab_ptr, const int *lab_idx,
-                             const int *z, int2 *rec, int *err) {
-    const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void set_z_kernel(long long n_work, const DocDesc *work, const long long *doc_ptr, const int *lab_idx,
+                             const int *z, int2 *R, int *err) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (d >= D) return;
-    const long long lab0 = lab_ptr[d];
-    const int A = (int)(lab_ptr[d + 1] - lab0);
-    for (long long n = doc_ptr[d] + lane; n < doc_ptr[d + 1]; n += 32) {
+    if (w >= n_work) return;
+    const DocDesc dd = work[w];
+    const long long src = doc_ptr[dd.doc];
+    for (int i = lane; i < dd.len; i += 32) {
         int j = -1;
-        for (int q = 0; q < A; ++q)
-            if (lab_idx[lab0 + q] == z[n]) { j = q; break; }
+        for (int q = 0; q < dd.A; ++q)
+            if (lab_idx[dd.lab0 + q] == z[src + i]) { j = q; break; }
         if (j < 0) { atomicExch(err, 1); j = 0; }
-        rec[n].y = REC_PACK(REC_F(rec[n].y), j);
+        int2 *r = R + dd.rbase + (long long)i * dd.stride;
+        r->y = REC_PACK(REC_F(r->y), j);
     }
 }
 
-__global__ void export_z_kernel(long long D, const long long *doc_ptr, const long long *lab_ptr,
-                                const int *lab_idx, const int2 *rec, int *z_out) {
-    const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void export_z_kernel(long long n_work, const DocDesc *work, const long long *doc_ptr, const int *lab_idx,
+                                const int2 *R, int *z_out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (d >= D) return;
-    const long long lab0 = lab_ptr[d];
-    for (long long n = doc_ptr[d] + lane; n < doc_ptr[d + 1]; n += 32)
-        z_out[n] = lab_idx[lab0 + REC_J(rec[n].y)];
+    if (w >= n_work) return;
+    const DocDesc dd = work[w];
+    const long long src = doc_ptr[dd.doc];
+    for (int i = lane; i < dd.len; i += 32)
+        z_out[src + i] = lab_idx[dd.lab0 + REC_J(R[dd.rbase + (long long)i * dd.stride].y)];
 }
 
 // n_wk += delta; delta = 0; n_k += column sums of delta.  blockDim = (ldk/4 capped to 256, rows per block).
@@ -542,12 +701,21 @@ __global__ void merge_delta_kernel(int4 *__restrict__ n_wk, int4 *__restrict__ d
     }
 }
 
-// Column sums of the word-major table: out[k] = sum_v n_wk[v][k]  (= row sums of the reference's n_k_v).
-__global__ void column_sums_kernel(const int *__restrict__ n_wk, int *__restrict__ out, int V, int ldk) {
-    for (int k = threadIdx.x; k < ldk; k += blockDim.x) {
-        int acc = 0;
-        for (int v = blockIdx.x; v < V; v += gridDim.x) acc += n_wk[(size_t)v * ldk + k];
-        if (acc) atomicAdd(&out[k], acc);
+// Column sums of the word-major table: out[k] += sum_v n_wk[v][k]  (= row sums of the reference's n_k_v).
+// Same thread layout as merge_delta_kernel; out must be zeroed by the caller.
+__global__ void column_sums_kernel(const int4 *__restrict__ n_wk, int *__restrict__ out, long long V, int ldk4, int K) {
+    for (int c4 = threadIdx.x; c4 < ldk4; c4 += blockDim.x) {
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V;
+             v += (long long)gridDim.x * blockDim.y) {
+            const int4 t = n_wk[(size_t)v * ldk4 + c4];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const int k = c4 * 4;
+        if (acc.x && k < K) atomicAdd(&out[k], acc.x);
+        if (acc.y && k + 1 < K) atomicAdd(&out[k + 1], acc.y);
+        if (acc.z && k + 2 < K) atomicAdd(&out[k + 2], acc.z);
+        if (acc.w && k + 3 < K) atomicAdd(&out[k + 3], acc.w);
     }
 }
 
@@ -574,7 +742,8 @@ __global__ void emit_phi_kernel(const int *__restrict__ n_wk, const int *__restr
     }
 }
 
-// theta[d][:] dense.  One warp per document; the row is zero-filled, then the active entries written.
+// theta[d][:] dense.  One warp per document (lab_ptr order = document order); the row is zero-filled, then the
+// active entries written.
 __global__ void emit_theta_kernel(long long D, const long long *lab_ptr, const int *lab_idx, const int *n_dk_act,
                                   double *theta, int K, double alpha, int smoothed) {
     const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -30,23 +30,22 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-uint32_t oracle_draw_word(uint64_t seed, uint32_t stream, uint32_t sweep, uint64_t t) {
-    uint64_t blk = t >> 2;
-    uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), sweep, stream};
+uint32_t oracle_draw_word(uint64_t seed, uint32_t stream, uint32_t sweep, uint64_t doc, uint64_t pos) {
+    uint32_t ctr[4] = {(uint32_t)(pos >> 2), (uint32_t)doc, sweep, stream};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t out[4];
     oracle_philox4x32_10(ctr, key, out);
-    return out[t & 3];
+    return out[pos & 3];
 }
 
 /* ------------------------------------------------------------------ init + histogram */
 int oracle_init_z(int64_t D, const int64_t *doc_ptr, const int64_t *lab_ptr, const int32_t *lab_idx,
-                  int32_t *z, uint64_t seed, uint64_t t_base) {
+                  int32_t *z, uint64_t seed, uint64_t doc_base) {
     for (int64_t d = 0; d < D; ++d) {
         uint64_t A = (uint64_t)(lab_ptr[d + 1] - lab_ptr[d]);
         if (A == 0) return -1;
         for (int64_t n = doc_ptr[d]; n < doc_ptr[d + 1]; ++n) {
-            uint32_t w = oracle_draw_word(seed, 1u, 0u, t_base + (uint64_t)n);
+            uint32_t w = oracle_draw_word(seed, 1u, 0u, doc_base + (uint64_t)d, (uint64_t)(n - doc_ptr[d]));
             z[n] = lab_idx[lab_ptr[d] + (int64_t)(((uint64_t)w * A) >> 32)];
         }
     }
@@ -86,7 +85,7 @@ int oracle_llda_exact_sweep(int64_t d_begin, int64_t d_end, const int64_t *doc_p
                             const int64_t *lab_ptr, const int32_t *lab_idx,
                             int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
                             int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
-                            uint64_t seed, uint32_t sweep, uint64_t t_base) {
+                            uint64_t seed, uint32_t sweep, uint64_t doc_base) {
     double *cum = (double *)malloc(sizeof(double) * (size_t)(K > 0 ? K : 1));
     if (!cum) return -2;
     const double vbeta = (double)V * beta;                 /* LabeledLDA.py:115  self.V * self.beta */
@@ -113,7 +112,7 @@ int oracle_llda_exact_sweep(int64_t d_begin, int64_t d_end, const int64_t *doc_p
                 cum[j] = run;
             }
             /* :118-119 replaced: inverse CDF on the unnormalised weights (see patched_reference.py) */
-            uint32_t x = oracle_draw_word(seed, 0u, sweep, t_base + (uint64_t)n);
+            uint32_t x = oracle_draw_word(seed, 0u, sweep, doc_base + (uint64_t)d, (uint64_t)(n - doc_ptr[d]));
             double u = ((double)x + 0.5) * (1.0 / 4294967296.0);
             double thr = u * run;
             int jn = A - 1;
@@ -131,6 +130,10 @@ int oracle_llda_exact_sweep(int64_t d_begin, int64_t d_end, const int64_t *doc_p
 
 /* ------------------------------------------------------------------ snapshot (doc-parallel, fp32) */
 
+/* Label lists of at most this many topics are summed serially (thread-per-document kernel); longer ones in
+ * 32-lane Kogge-Stone chunks (group-per-document kernels).  Must equal GIBBS_SERIAL_MAX in llda_kernels.cuh. */
+#define ORACLE_SERIAL_MAX 8
+
 /* Inclusive scan of x[0..31] in the order a 32-lane Kogge-Stone __shfl_up scan produces. */
 static void ks_scan32(float *x) {
     for (int off = 1; off < 32; off <<= 1) {
@@ -146,7 +149,7 @@ static int snapshot_doc(int64_t d, const int64_t *doc_ptr, const int32_t *word, 
                         float alpha_f, float beta_f, float vbeta_f,
                         const int32_t *n_wk, int32_t *n_dk_act, const int32_t *n_k,
                         int32_t *delta_wk, int32_t *delta_k,
-                        uint64_t seed, uint32_t sweep, uint64_t t_base,
+                        uint64_t seed, uint32_t sweep, uint64_t doc_base,
                         int32_t *nkb, float *cum) {
     const int32_t *lab = lab_idx + lab_ptr[d];
     int32_t *ndk = n_dk_act + lab_ptr[d];
@@ -159,6 +162,23 @@ static int snapshot_doc(int64_t d, const int64_t *doc_ptr, const int32_t *word, 
         if (jo < 0) return -1;
         const int32_t *row = n_wk + (size_t)v * ldk;
         float carry = 0.0f, total = 0.0f;
+        if (A <= ORACLE_SERIAL_MAX) {
+            /* short label lists: one thread owns the document and adds the weights left to right */
+            float run = 0.0f;
+            for (int j = 0; j < A; ++j) {
+                int32_t self = (j == jo) ? f : 0;
+                int32_t nd = ndk[j] - self;
+                int32_t nw = row[lab[j]] - self;
+                float a = (float)nd + alpha_f;
+                float b = (float)nw + beta_f;
+                float cc = (float)(nkb[j] + nd) + vbeta_f;
+                float ab = a * b;
+                float w = ab / cc;
+                run = run + w;
+                cum[j] = run;
+            }
+            total = run;
+        } else
         for (int c = 0; c < nchunk; ++c) {
             float x[32];
             for (int l = 0; l < 32; ++l) {
@@ -184,7 +204,7 @@ static int snapshot_doc(int64_t d, const int64_t *doc_ptr, const int32_t *word, 
             if (c == nchunk - 1) total = cum[A - 1];
             carry = carry + x[31];
         }
-        uint32_t xw = oracle_draw_word(seed, 0u, sweep, t_base + (uint64_t)n);
+        uint32_t xw = oracle_draw_word(seed, 0u, sweep, doc_base + (uint64_t)d, (uint64_t)(n - doc_ptr[d]));
         float u = (float)(xw >> 8) * (1.0f / 16777216.0f);
         float thr = u * total;
         int jn = A - 1;
@@ -220,7 +240,7 @@ int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t
                                int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx,
                                int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
                                int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
-                               uint64_t seed, uint32_t sweep, uint64_t t_base, int32_t n_threads) {
+                               uint64_t seed, uint32_t sweep, uint64_t doc_base, int32_t n_threads) {
     if (n_blocks < 1) n_blocks = 1;
     if (n_threads < 1) n_threads = 1;
     const float alpha_f = (float)alpha, beta_f = (float)beta, vbeta_f = (float)((double)V * beta);
@@ -239,7 +259,7 @@ int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t
                 for (int64_t d = tile_rng[2 * i]; d < tile_rng[2 * i + 1]; ++d) {
                     int r = snapshot_doc(d, doc_ptr, word, freq, z, lab_ptr, lab_idx, ldk,
                                          alpha_f, beta_f, vbeta_f, n_wk, n_dk_act, n_k,
-                                         delta_wk, delta_k, seed, sweep, t_base, nkb, cum);
+                                         delta_wk, delta_k, seed, sweep, doc_base, nkb, cum);
                     if (r) {
 #pragma omp atomic write
                         err = r;

@@ -33,13 +33,14 @@ extern "C" {
 
 /* Philox4x32-10 (Random123).  */
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* One 32-bit word per (seed, stream, sweep, draw index t); see oracle/philox.py for the addressing. */
-uint32_t oracle_draw_word(uint64_t seed, uint32_t stream, uint32_t sweep, uint64_t t);
+/* One 32-bit word per (seed, stream, sweep, global document id, position of the draw inside the document);
+ * see oracle/philox.py for the addressing. */
+uint32_t oracle_draw_word(uint64_t seed, uint32_t stream, uint32_t sweep, uint64_t doc, uint64_t pos);
 
 /* z ~ Uniform(labels of the doc): z = lab_idx[lab_ptr[d] + ((word * A) >> 32)], stream 1.
  * Device-side replacement of LabeledLDA.py:86-87 for synthetic scale runs. */
 int oracle_init_z(int64_t D, const int64_t *doc_ptr, const int64_t *lab_ptr, const int32_t *lab_idx,
-                  int32_t *z, uint64_t seed, uint64_t t_base);
+                  int32_t *z, uint64_t seed, uint64_t doc_base);
 
 /* Histogram z -> counts (LabeledLDA.py:89-92, CascadeLDA.py:382-385, HSLDA.py:127-130). */
 int oracle_counts_build(int64_t D, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
@@ -54,12 +55,14 @@ int oracle_llda_exact_sweep(int64_t d_begin, int64_t d_end, const int64_t *doc_p
                             const int64_t *lab_ptr, const int32_t *lab_idx,
                             int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
                             int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
-                            uint64_t seed, uint32_t sweep, uint64_t t_base);
+                            uint64_t seed, uint32_t sweep, uint64_t doc_base);
 
 /* One sweep of the document-parallel `snapshot` schedule in fp32: every draw reads
  * n_wk frozen at the start of its refresh block, the document's own live n_dk, and
  * n_k(frozen) + (n_dk(live) - n_dk(block start)).  Tile i is the document range
  * [tile_rng[2i], tile_rng[2i+1]) (empty ranges allowed); tiles with i % n_blocks == b form block b.
+ * Weights of a document with at most 8 active topics are added left to right; longer label lists in 32-wide
+ * Kogge-Stone chunks -- the two summation orders of the device kernels.
  * n_threads > 1 runs the documents of a block concurrently (the result does not depend on it). */
 /* 0 when built without OpenMP, else omp_get_max_threads(). */
 int oracle_openmp_threads(void);
@@ -68,7 +71,7 @@ int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t
                                int32_t *z, const int64_t *lab_ptr, const int32_t *lab_idx,
                                int32_t K, int32_t V, int32_t ldk, double alpha, double beta,
                                int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
-                               uint64_t seed, uint32_t sweep, uint64_t t_base, int32_t n_threads);
+                               uint64_t seed, uint32_t sweep, uint64_t doc_base, int32_t n_threads);
 
 #ifdef __cplusplus
 }

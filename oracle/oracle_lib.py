@@ -31,7 +31,7 @@ def load():
     i32, i64, u32, u64, dbl = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
     lib.oracle_philox4x32_10.argtypes = [u32p, u32p, u32p]
     lib.oracle_philox4x32_10.restype = None
-    lib.oracle_draw_word.argtypes = [u64, u32, u32, u64]
+    lib.oracle_draw_word.argtypes = [u64, u32, u32, u64, u64]
     lib.oracle_draw_word.restype = u32
     lib.oracle_openmp_threads.restype = C.c_int
     lib.oracle_init_z.argtypes = [i64, i64p, i64p, i32p, i32p, u64, u64]
@@ -75,7 +75,7 @@ def openmp_threads():
 class LldaOracle(object):
     """Host mirror of one device shard: owns z and the three count arrays in the device layout."""
 
-    def __init__(self, doc_ptr, word, freq, lab_ptr, lab_idx, K, V, alpha, beta, seed=0, z=None, t_base=0):
+    def __init__(self, doc_ptr, word, freq, lab_ptr, lab_idx, K, V, alpha, beta, seed=0, z=None, doc_base=0):
         self.lib = load()
         self.doc_ptr = _a(doc_ptr, np.int64)
         self.word = _a(word, np.int32)
@@ -85,12 +85,12 @@ class LldaOracle(object):
         self.D = self.doc_ptr.shape[0] - 1
         self.N = int(self.doc_ptr[-1])
         self.K, self.V, self.ldk = int(K), int(V), ldk_of(K)
-        self.alpha, self.beta, self.seed, self.t_base = float(alpha), float(beta), int(seed), int(t_base)
+        self.alpha, self.beta, self.seed, self.doc_base = float(alpha), float(beta), int(seed), int(doc_base)
         self.sweep = 0
         if z is None:
             self.z = np.zeros(self.N, dtype=np.int32)
             rc = self.lib.oracle_init_z(self.D, _p(self.doc_ptr, i64p), _p(self.lab_ptr, i64p), _p(self.lab_idx, i32p),
-                                        _p(self.z, i32p), self.seed, self.t_base)
+                                        _p(self.z, i32p), self.seed, self.doc_base)
             if rc:
                 raise RuntimeError("oracle_init_z failed (%d)" % rc)
         else:
@@ -124,19 +124,20 @@ class LldaOracle(object):
                                                   _p(self.freq, i32p), _p(self.z, i32p), _p(self.lab_ptr, i64p),
                                                   _p(self.lab_idx, i32p), self.K, self.V, self.ldk, self.alpha,
                                                   self.beta, _p(self.n_wk_pad, i32p), _p(self.n_dk_act, i32p),
-                                                  _p(self.n_k, i32p), self.seed, self.sweep, self.t_base)
+                                                  _p(self.n_k, i32p), self.seed, self.sweep, self.doc_base)
             if rc:
                 raise RuntimeError("oracle_llda_exact_sweep failed (%d)" % rc)
             self.sweep += 1
 
-    def snapshot_sweep(self, n=1, n_refresh=1, tile_docs=256, tile_base=0, n_threads=1):
-        """Tiles are `tile_docs` consecutive documents; tile i belongs to block (tile_base + i) % n_refresh."""
-        n_tiles = (self.D + tile_docs - 1) // tile_docs
+    def snapshot_sweep(self, n=1, n_refresh=1, tile_docs=256, n_threads=1):
+        """Tiles are `tile_docs` consecutive GLOBAL document ids; tile i belongs to block i % n_refresh."""
+        first_tile = self.doc_base // tile_docs
+        n_tiles = (self.doc_base + self.D + tile_docs - 1) // tile_docs - first_tile
         # order tiles so that `i % n_blocks == b` in the C code selects block (tile_base + i) % n_refresh:
         # the C routine takes an explicit tile list, so pass tiles grouped by block, round-robin interleaved.
         tiles_by_block = [[] for _ in range(n_refresh)]
         for i in range(n_tiles):
-            tiles_by_block[(tile_base + i) % n_refresh].append(i)
+            tiles_by_block[(first_tile + i) % n_refresh].append(i)
         width = max([len(t) for t in tiles_by_block] + [1])
         order = []
         for r in range(width):
@@ -145,15 +146,15 @@ class LldaOracle(object):
         tile_rng = np.zeros((len(order), 2), dtype=np.int64)
         for q, i in enumerate(order):
             if i >= 0:
-                tile_rng[q, 0] = i * tile_docs
-                tile_rng[q, 1] = min(self.D, (i + 1) * tile_docs)
+                tile_rng[q, 0] = max(0, (first_tile + i) * tile_docs - self.doc_base)
+                tile_rng[q, 1] = min(self.D, (first_tile + i + 1) * tile_docs - self.doc_base)
         for _ in range(n):
             rc = self.lib.oracle_llda_snapshot_sweep(len(order), _p(tile_rng, i64p), n_refresh, _p(self.doc_ptr, i64p),
                                                      _p(self.word, i32p), _p(self.freq, i32p), _p(self.z, i32p),
                                                      _p(self.lab_ptr, i64p), _p(self.lab_idx, i32p), self.K, self.V,
                                                      self.ldk, self.alpha, self.beta, _p(self.n_wk_pad, i32p),
                                                      _p(self.n_dk_act, i32p), _p(self.n_k, i32p), self.seed, self.sweep,
-                                                     self.t_base, n_threads)
+                                                     self.doc_base, n_threads)
             if rc:
                 raise RuntimeError("oracle_llda_snapshot_sweep failed (%d)" % rc)
             self.sweep += 1

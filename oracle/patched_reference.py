@@ -15,7 +15,7 @@ What is patched, and why
         k = first index with cumsum(prob)[k] > u * cumsum(prob)[-1]
 
     with u = (word + 0.5) * 2^-32 and word = Philox4x32-10 addressed as in oracle/philox.py
-    (stream 0, the sweep number, the draw's index in corpus order).
+    (stream 0, the sweep number, the document's index and the draw's position inside the document).
 """
 import importlib
 import os
@@ -63,11 +63,15 @@ class PhiloxDraw(object):
         self._words = None
         self.calls = 0
 
-    def begin_sweep(self, sweep, n_draws, t_base=0):
+    def begin_sweep(self, sweep, doc_lens, doc_base=0):
+        """doc_lens[d] = draws of document d; the draw at position p of document d uses word (doc_base + d, p)."""
         self.sweep = int(sweep)
         self.t = 0
-        self._words = philox.draw_words(self.seed, self.stream, self.sweep,
-                                        np.arange(t_base, t_base + n_draws, dtype=np.uint64))
+        doc_lens = np.asarray(doc_lens, dtype=np.int64)
+        doc = np.repeat(np.arange(doc_lens.shape[0], dtype=np.int64), doc_lens)
+        starts = np.cumsum(doc_lens) - doc_lens
+        pos = np.arange(doc.shape[0], dtype=np.int64) - starts[doc]
+        self._words = philox.draw_words(self.seed, self.stream, self.sweep, doc + doc_base, pos)
 
     def __call__(self, n, prob):
         assert n == 1
@@ -114,7 +118,7 @@ def run_llda_sweeps(module, model, draw, n_sweeps, first_sweep=0):
     n_draws = sum(len(d) for d in model.docs)
     out = []
     for s in range(first_sweep, first_sweep + n_sweeps):
-        draw.begin_sweep(s, n_draws)
+        draw.begin_sweep(s, [len(d) for d in model.docs])
         model.training_iteration()
         assert draw.t == n_draws, "exactly one draw per pair per sweep"
         out.append(llda_state(model))

@@ -9,10 +9,13 @@ Philox-4x32 with 10 rounds, as published in Random123 (philox.h).  Pinned by the
 Random123 known-answer vectors quoted in SURVEY.md §8(c)3 (see tests/test_philox.py).
 
 Draw addressing used by every sampler in this repo (GPU, C oracle, patched
-reference) -- one 32-bit word per (stream, sweep, draw index t):
+reference) -- one 32-bit word per (stream, sweep, global document id d, position p of the draw in d):
 
-    ctr = (lo32(t >> 2), hi32(t >> 2), sweep, stream)    key = (lo32(seed), hi32(seed))
-    word = philox4x32_10(ctr, key)[t & 3]
+    ctr = (p >> 2, d, sweep, stream)    key = (lo32(seed), hi32(seed))
+    word = philox4x32_10(ctr, key)[p & 3]
+
+(addressing by document keeps the stream independent of how documents are sharded over GPUs, and
+lets a thread that walks one document reuse each Philox block for four consecutive draws)
 
 The reference itself never seeds its RNG, so this addressing is the
 repo's own convention; what it replaces is the single ``multinom_draw(1, prob)`` call
@@ -49,24 +52,25 @@ def philox4x32_10(ctr, key):
     return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)
 
 
-def draw_words(seed, stream, sweep, t):
-    """32-bit word for each draw index in ``t`` (array-like of int64)."""
-    t = np.atleast_1d(np.asarray(t, dtype=np.uint64))
-    blk = t >> np.uint64(2)
-    ctr = np.empty(t.shape + (4,), dtype=np.uint64)
-    ctr[..., 0] = blk & MASK32
-    ctr[..., 1] = blk >> np.uint64(32)
+def draw_words(seed, stream, sweep, doc, pos):
+    """32-bit word for each (global document id, position inside the document) pair (array-likes)."""
+    doc = np.atleast_1d(np.asarray(doc, dtype=np.uint64))
+    pos = np.atleast_1d(np.asarray(pos, dtype=np.uint64))
+    doc, pos = np.broadcast_arrays(doc, pos)
+    ctr = np.empty(pos.shape + (4,), dtype=np.uint64)
+    ctr[..., 0] = (pos >> np.uint64(2)) & MASK32
+    ctr[..., 1] = doc & MASK32
     ctr[..., 2] = np.uint64(sweep & 0xFFFFFFFF)
     ctr[..., 3] = np.uint64(stream & 0xFFFFFFFF)
-    key = np.empty(t.shape + (2,), dtype=np.uint64)
+    key = np.empty(pos.shape + (2,), dtype=np.uint64)
     key[..., 0] = np.uint64(seed & 0xFFFFFFFF)
     key[..., 1] = np.uint64((seed >> 32) & 0xFFFFFFFF)
     out = philox4x32_10(ctr, key)
-    return np.take_along_axis(out, (t & np.uint64(3)).astype(np.int64)[..., None], axis=-1)[..., 0]
+    return np.take_along_axis(out, (pos & np.uint64(3)).astype(np.int64)[..., None], axis=-1)[..., 0]
 
 
-def draw_word(seed, stream, sweep, t):
-    return int(draw_words(seed, stream, sweep, [t])[0])
+def draw_word(seed, stream, sweep, doc, pos):
+    return int(draw_words(seed, stream, sweep, [doc], [pos])[0])
 
 
 def u01_f64(word):

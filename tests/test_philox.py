@@ -24,16 +24,21 @@ def test_philox_c_oracle_kat(oracle):
 
 
 def test_draw_word_addressing(oracle):
-    """C oracle and NumPy restatement agree on the (seed, stream, sweep, t) -> word addressing."""
+    """C oracle and NumPy restatement agree on the (seed, stream, sweep, doc, pos) -> word addressing."""
     import philox
     lib = oracle.load()
     seed = 0x1234567890abcdef
-    t = np.array([0, 1, 2, 3, 4, 5, 1023, 2**32 + 7, 2**40 + 3], dtype=np.uint64)
+    doc = np.array([0, 0, 0, 0, 0, 7, 7, 1023, 2**31 + 5, 2**32 - 1], dtype=np.uint64)
+    pos = np.array([0, 1, 2, 3, 4, 5, 1023, 77, 2**20 + 3, 9], dtype=np.uint64)
     for stream in (0, 1, 2):
         for sweep in (0, 1, 77):
-            want = philox.draw_words(seed, stream, sweep, t)
-            got = [lib.oracle_draw_word(seed, stream, sweep, int(x)) for x in t]
+            want = philox.draw_words(seed, stream, sweep, doc, pos)
+            got = [lib.oracle_draw_word(seed, stream, sweep, int(d), int(q)) for d, q in zip(doc, pos)]
             assert [int(w) for w in want] == got
+    # four consecutive positions of one document share one Philox block
+    blk = philox.philox4x32_10(np.array([5, 9, 3, 0], dtype=np.uint32),
+                               np.array([seed & 0xffffffff, seed >> 32], dtype=np.uint32))
+    assert [int(x) for x in blk] == [lib.oracle_draw_word(seed, 0, 3, 9, 20 + i) for i in range(4)]
 
 
 @pytest.mark.gpu
