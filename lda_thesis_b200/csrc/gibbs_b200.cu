@@ -509,7 +509,7 @@ static int merge_block(gibbs_handle *h) {
     int bx = std::min(256, (ldk4 + 31) / 32 * 32);
     int by = std::max(1, 256 / bx);
     dim3 block(bx, by);
-    unsigned grid = (unsigned)std::min<long long>((h->desc.V + by - 1) / by, (long long)h->sm_count * 8);
+    unsigned grid = (unsigned)std::min<long long>((h->desc.V + by * 4 - 1) / (by * 4), (long long)h->sm_count * 8);
     merge_delta_kernel<<<grid, block, 0, h->stream>>>(reinterpret_cast<int4 *>(h->n_wk.p), reinterpret_cast<int4 *>(h->delta_wk.p),
                                                       h->n_k.p, h->desc.V, ldk4, h->desc.K);
     CK(cudaGetLastError());

@@ -676,21 +676,32 @@ __global__ void export_z_kernel(long long n_work, const DocDesc *work, const lon
 }
 
 // n_wk += delta; delta = 0; n_k += column sums of delta.  blockDim = (ldk/4 capped to 256, rows per block).
-// Thread (x, y) owns int4 column chunks x, x + blockDim.x, ... so its topic columns are fixed.
-__global__ void merge_delta_kernel(int4 *__restrict__ n_wk, int4 *__restrict__ delta, int *__restrict__ n_k,
-                                   long long V, int ldk4, int K) {
+// Thread (x, y) owns int4 column chunks x, x + blockDim.x, ... so its topic columns are fixed; four rows are in
+// flight per thread (both tables are read unconditionally) so the pass runs at memory speed; untouched 16-byte chunks
+// are not written.
+__global__ void __launch_bounds__(256) merge_delta_kernel(int4 *__restrict__ n_wk, int4 *__restrict__ delta,
+                                                          int *__restrict__ n_k, long long V, int ldk4, int K) {
+    const long long stride = (long long)gridDim.x * blockDim.y;
     for (int c4 = threadIdx.x; c4 < ldk4; c4 += blockDim.x) {
         int4 acc = make_int4(0, 0, 0, 0);
-        for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V;
-             v += (long long)gridDim.x * blockDim.y) {
-            const size_t idx = (size_t)v * ldk4 + c4;
-            const int4 dl = delta[idx];
-            if (dl.x | dl.y | dl.z | dl.w) {
-                int4 t = n_wk[idx];
-                t.x += dl.x; t.y += dl.y; t.z += dl.z; t.w += dl.w;
-                n_wk[idx] = t;
-                delta[idx] = make_int4(0, 0, 0, 0);
-                acc.x += dl.x; acc.y += dl.y; acc.z += dl.z; acc.w += dl.w;
+        for (long long v0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; v0 < V; v0 += 4 * stride) {
+            int4 dl[4], t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {      // eight independent 16-byte loads in flight per thread
+                const long long v = v0 + u * stride;
+                const size_t idx = (size_t)v * ldk4 + c4;
+                dl[u] = (v < V) ? delta[idx] : make_int4(0, 0, 0, 0);
+                t[u] = (v < V) ? n_wk[idx] : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (dl[u].x | dl[u].y | dl[u].z | dl[u].w) {
+                    const size_t idx = (size_t)(v0 + u * stride) * ldk4 + c4;
+                    t[u].x += dl[u].x; t[u].y += dl[u].y; t[u].z += dl[u].z; t[u].w += dl[u].w;
+                    n_wk[idx] = t[u];
+                    delta[idx] = make_int4(0, 0, 0, 0);
+                    acc.x += dl[u].x; acc.y += dl[u].y; acc.z += dl[u].z; acc.w += dl[u].w;
+                }
             }
         }
         const int k = c4 * 4;
