@@ -11,7 +11,9 @@
  *   gibbs_hslda_*        HSLDA.py:171-272 sample_z
  *   gibbs_emit_phi       LabeledLDA.py:231-234 get_phi, CascadeLDA.py:394-395 get_ph, HSLDA.py:151-152
  *   gibbs_emit_theta     LabeledLDA.py:236-239 get_theta, HSLDA.py:148-149 get_zbar
- *   gibbs_test_*         LabeledLDA.py:179-212 run_test, CascadeLDA.py:210-247 cascade_test (frozen phi)
+ *   gibbs_test_*         LabeledLDA.py:155-212 prep4test + run_test, CascadeLDA.py:186-247 cascade_test (frozen phi)
+ *   gibbs_thin_*         LabeledLDA.py:138-145, CascadeLDA.py:430-434, HSLDA.py:327-333 (thinning mean)
+ *   gibbs_perplexity     LabeledLDA.py:256-265
  *
  * Conventions
  *   - plain C, no torch/NumPy types; the caller owns every host buffer, the handle owns all device memory
@@ -168,11 +170,34 @@ int gibbs_set_sweep_counter(gibbs_t *h, uint32_t sweep);
 int gibbs_hslda_set(gibbs_t *h, int32_t L, const double *eta, const double *a_act, const double *mean_a_act,
                     const double *alpha_beta);
 
-/* Frozen-phi test chains (LabeledLDA.py:179-212): independent documents, `it` sweeps, thinning mean of
- * n_dk / sum(n_dk) written to th_hat[D_test][K].  phi_KV is [K][V] fp64 as produced by gibbs_emit_phi. */
-int gibbs_test_chains(int32_t device, int32_t K, int32_t V, double alpha, const double *phi_KV,
-                      int64_t D_test, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
-                      const int32_t *z_init, int32_t it, int32_t thinning, uint64_t seed, double *th_hat);
+/* Thinning running mean kept on the device (LabeledLDA.py:138-145, CascadeLDA.py:430-434, HSLDA.py:327-333):
+ *   hat = c_old * hat + c_new * current     (the first call after gibbs_load stores `current`)
+ * `what`: bit 0 = phi [K][V] (smoothed as in gibbs_emit_phi), bit 1 = theta over the label lists (gibbs_emit_theta_csr).
+ * The host class passes the reference's own coefficients ((s-1)/s, 1/s) so every rounding matches NumPy's. */
+int gibbs_thin_accumulate(gibbs_t *h, double c_old, double c_new, int32_t smoothed, int32_t what);
+int gibbs_thin_get(gibbs_t *h, double *ph_hat_KV, double *th_hat_act);   /* either pointer may be NULL */
+
+/* Training perplexity of LabeledLDA.py:256-265 from the live counts: *neg_log_sum = -sum over (doc, unique word) pairs of
+ * log(phi[:, w] . theta_d), *n_pairs = number of pairs; perplexity = exp(neg_log_sum / n_pairs). */
+int gibbs_perplexity(gibbs_t *h, double *neg_log_sum, int64_t *n_pairs);
+
+/* Frozen-phi test chains: LabeledLDA.py:155-212 (prep4test + run_test), CascadeLDA.py:186-247 (prep4test + cascade_test).
+ * The handle keeps a word-major device copy of phi_KV ([K][V] fp64, e.g. model.ph_hat / model.ph).
+ * A chain is one (document, topic list) pair; chains are independent.  lab_ptr/lab_idx == NULL: every chain uses all K
+ * topics and th_hat is [n_chains][K]; otherwise th_hat is aligned with lab_idx.
+ *   init_mode 0: z holds the start state (global topic ids)
+ *             1: z ~ phi[:, v] (LabeledLDA.py:162-175)
+ *             2: z ~ (phi[:, v] + beta_fb) / sum with the first list entry's weight set to 1 / len(doc) (CascadeLDA.py:194-206)
+ *   beta_fb > 0: when every weight of a draw is zero, redraw from (n_dk + alpha) * (phi + beta_fb) (CascadeLDA.py:225-230)
+ * th_hat: thinning mean of n_dk / sum(n_dk) over iterations i with (i + 1) % thinning == 0; zeros if none.
+ * z (optional unless init_mode 0) receives the final assignments.  RNG: stream 2 / 4, counter (iteration, chain_base + chain, position). */
+typedef struct gibbs_test_handle gibbs_test_t;
+int  gibbs_test_create(gibbs_test_t **out, int32_t device, int32_t K, int32_t V, const double *phi_KV);
+void gibbs_test_destroy(gibbs_test_t *t);
+int  gibbs_test_run(gibbs_test_t *t, double alpha, double beta_fb, int64_t n_chains, const int64_t *doc_ptr,
+                    const int32_t *word, const int32_t *freq, const int64_t *lab_ptr, const int32_t *lab_idx,
+                    int32_t *z, int32_t init_mode, int32_t it, int32_t thinning, uint64_t seed, int64_t chain_base,
+                    double *th_hat);
 
 /* Known-answer hook: Philox4x32-10 evaluated ON THE DEVICE for n (ctr,key) pairs. */
 int gibbs_philox_kat(int32_t device, int32_t n, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4);

@@ -73,13 +73,20 @@ def load_library():
     lib.gibbs_stats.argtypes = [vp, _p(GibbsStats)]
     lib.gibbs_set_sweep_counter.argtypes = [vp, C.c_uint32]
     lib.gibbs_hslda_set.argtypes = [vp, i32, _p(dbl), _p(dbl), _p(dbl), _p(dbl)]
-    lib.gibbs_test_chains.argtypes = [i32, i32, i32, dbl, _p(dbl), i64, _p(i64), _p(i32), _p(i32), _p(i32), i32, i32,
-                                      u64, _p(dbl)]
+    lib.gibbs_thin_accumulate.argtypes = [vp, dbl, dbl, i32, i32]
+    lib.gibbs_thin_get.argtypes = [vp, _p(dbl), _p(dbl)]
+    lib.gibbs_perplexity.argtypes = [vp, _p(dbl), _p(i64)]
+    lib.gibbs_test_create.argtypes = [_p(vp), i32, i32, i32, _p(dbl)]
+    lib.gibbs_test_destroy.argtypes = [vp]
+    lib.gibbs_test_destroy.restype = None
+    lib.gibbs_test_run.argtypes = [vp, dbl, dbl, i64, _p(i64), _p(i32), _p(i32), _p(i64), _p(i32), _p(i32), i32, i32, i32,
+                                   u64, i64, _p(dbl)]
     lib.gibbs_philox_kat.argtypes = [i32, i32, _p(C.c_uint32), _p(C.c_uint32), _p(C.c_uint32)]
     for name in ("gibbs_create", "gibbs_load", "gibbs_sweep", "gibbs_comm_unique_id", "gibbs_comm_init",
                  "gibbs_emit_theta_csr", "gibbs_trim", "gibbs_stream", "gibbs_get_state", "gibbs_set_z", "gibbs_add_counts", "gibbs_emit_phi",
                  "gibbs_emit_theta", "gibbs_stats", "gibbs_set_sweep_counter", "gibbs_hslda_set",
-                 "gibbs_test_chains", "gibbs_philox_kat"):
+                 "gibbs_thin_accumulate", "gibbs_thin_get", "gibbs_perplexity", "gibbs_test_create", "gibbs_test_run",
+                 "gibbs_philox_kat"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
@@ -264,6 +271,23 @@ class GibbsSampler(object):
         _check(self._lib.gibbs_emit_theta(self._h, _ptr(out, C.c_double), 1 if smoothed else 0), "gibbs_emit_theta")
         return out
 
+    def thin_accumulate(self, c_old, c_new, smoothed=True, phi=True, theta=True):
+        """hat = c_old * hat + c_new * current on the device (first call after load: hat = current)."""
+        _check(self._lib.gibbs_thin_accumulate(self._h, float(c_old), float(c_new), 1 if smoothed else 0,
+                                               (1 if phi else 0) | (2 if theta else 0)), "gibbs_thin_accumulate")
+
+    def thin_get(self, phi=True, theta=True):
+        ph = np.empty((self.K, self.V), dtype=np.float64) if phi else None
+        th = np.empty(self.n_lab, dtype=np.float64) if theta else None
+        _check(self._lib.gibbs_thin_get(self._h, _ptr(ph, C.c_double), _ptr(th, C.c_double)), "gibbs_thin_get")
+        return ph, th
+
+    def perplexity(self):
+        """LabeledLDA.py:256-265 on the live counts."""
+        s, n = C.c_double(), C.c_int64()
+        _check(self._lib.gibbs_perplexity(self._h, C.byref(s), C.byref(n)), "gibbs_perplexity")
+        return float(np.exp(s.value / n.value)) if n.value else float("nan")
+
     def stats(self):
         st = GibbsStats()
         _check(self._lib.gibbs_stats(self._h, C.byref(st)), "gibbs_stats")
@@ -283,21 +307,64 @@ class GibbsSampler(object):
                "gibbs_hslda_set")
 
 
-def test_chains(K, V, alpha, phi_KV, doc_ptr, word, freq, z_init, it, thinning, seed=0, device=0):
-    """Frozen-phi test chains (LabeledLDA.py:179-212) -> th_hat [D_test, K]."""
-    lib = load_library()
-    phi_KV = _arr(phi_KV, np.float64)
-    doc_ptr = _arr(doc_ptr, np.int64)
-    word = _arr(word, np.int32)
-    freq = None if freq is None else _arr(freq, np.int32)
-    z_init = _arr(z_init, np.int32)
-    D = doc_ptr.shape[0] - 1
-    out = np.zeros((D, K), dtype=np.float64)
-    _check(lib.gibbs_test_chains(int(device), int(K), int(V), float(alpha), _ptr(phi_KV, C.c_double), D,
-                                 _ptr(doc_ptr, C.c_int64), _ptr(word, C.c_int32), _ptr(freq, C.c_int32),
-                                 _ptr(z_init, C.c_int32), int(it), int(thinning), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                 _ptr(out, C.c_double)), "gibbs_test_chains")
-    return out
+TEST_INIT = {"given": 0, "llda": 1, "cascade": 2}
+
+
+class TestChains(object):
+    """Frozen-phi test chains (LabeledLDA.py:155-212, CascadeLDA.py:186-247): a device copy of phi + gibbs_test_run."""
+    __test__ = False          # not a pytest class
+
+    def __init__(self, phi_KV, device=0):
+        lib = load_library()
+        self._lib = lib
+        phi_KV = _arr(phi_KV, np.float64)
+        if phi_KV.ndim != 2:
+            raise ValueError("phi must be [K, V]")
+        self.K, self.V = int(phi_KV.shape[0]), int(phi_KV.shape[1])
+        self._t = C.c_void_p()
+        _check(lib.gibbs_test_create(C.byref(self._t), int(device), self.K, self.V, _ptr(phi_KV, C.c_double)),
+               "gibbs_test_create")
+
+    def close(self):
+        if getattr(self, "_t", None) is not None and self._t:
+            self._lib.gibbs_test_destroy(self._t)
+            self._t = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, doc_ptr, word, freq, it, thinning, alpha, lab_ptr=None, lab_idx=None, z_init=None, init="llda",
+            beta_fb=0.0, seed=0, chain_base=0):
+        """-> (th_hat, z).  th_hat is [n_chains, K] without topic lists, else aligned with lab_idx."""
+        doc_ptr = _arr(doc_ptr, np.int64)
+        word = _arr(word, np.int32)
+        freq = None if freq is None else _arr(freq, np.int32)
+        n = doc_ptr.shape[0] - 1
+        N = int(doc_ptr[-1]) if n >= 0 else 0
+        if word.shape[0] != N or (freq is not None and freq.shape[0] != N):
+            raise ValueError("array lengths do not match the CSR offsets")
+        if lab_ptr is not None:
+            lab_ptr, lab_idx = _arr(lab_ptr, np.int64), _arr(lab_idx, np.int32)
+            if lab_ptr.shape[0] != n + 1 or lab_idx.shape[0] != int(lab_ptr[-1]):
+                raise ValueError("lab_ptr / lab_idx do not match")
+            th = np.zeros(int(lab_ptr[-1]), dtype=np.float64)
+        else:
+            th = np.zeros((n, self.K), dtype=np.float64)
+        if init == "given":
+            z = _arr(z_init, np.int32).copy()
+            if z.shape[0] != N:
+                raise ValueError("z_init must have one entry per draw")
+        else:
+            z = np.zeros(N, dtype=np.int32)
+        _check(self._lib.gibbs_test_run(self._t, float(alpha), float(beta_fb), n, _ptr(doc_ptr, C.c_int64),
+                                        _ptr(word, C.c_int32), _ptr(freq, C.c_int32), _ptr(lab_ptr, C.c_int64),
+                                        _ptr(lab_idx, C.c_int32), _ptr(z, C.c_int32), TEST_INIT[init], int(it),
+                                        int(thinning), int(seed) & 0xFFFFFFFFFFFFFFFF, int(chain_base),
+                                        _ptr(th, C.c_double)), "gibbs_test_run")
+        return th, z
 
 
 def philox_kat(ctr4, key2, device=0):

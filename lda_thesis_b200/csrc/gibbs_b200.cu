@@ -63,6 +63,8 @@ struct gibbs_handle {
     DevBuf<unsigned long long> counters;   // [0] work counter, [1] changed
     DevBuf<int> err_flag;
     DevBuf<unsigned char> scratch;         // uploads, z export, phi/theta staging
+    DevBuf<double> hat_phi, hat_theta, doc_sum;   // thinning means (gibbs_thin_accumulate), perplexity partials
+    bool hat_phi_set = false, hat_theta_set = false;
     std::vector<DocList> lists;            // [block * N_BINS + bin]
     long long bin_draws[N_BINS] = {0};
     // multi-GPU
@@ -147,6 +149,7 @@ extern "C" void gibbs_destroy(gibbs_t *h) {
     release(h, h->work); release(h, h->rec); release(h, h->n_wk); release(h, h->delta_wk);
     release(h, h->n_k); release(h, h->n_dk_act); release(h, h->colsum); release(h, h->counters);
     release(h, h->err_flag); release(h, h->scratch);
+    release(h, h->hat_phi); release(h, h->hat_theta); release(h, h->doc_sum);
     hslda_free(&h->hs);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
@@ -184,7 +187,7 @@ static int column_sums(gibbs_handle *h, int *out) {
     int by = std::max(1, 256 / bx);
     unsigned grid = (unsigned)std::min<long long>((h->desc.V + by - 1) / by, (long long)h->sm_count * 8);
     CK(cudaMemsetAsync(out, 0, sizeof(int) * (size_t)h->desc.K, h->stream));
-    column_sums_kernel<<<grid, dim3(bx, by), 0, h->stream>>>(reinterpret_cast<const int4 *>(h->n_wk.p), out, h->desc.V, ldk4, h->desc.K);
+    column_sums_kernel<<<grid, dim3(bx, by), sizeof(int) * (size_t)h->ldk, h->stream>>>(reinterpret_cast<const int4 *>(h->n_wk.p), out, h->desc.V, ldk4, h->desc.K);
     CK(cudaGetLastError());
     return 0;
 }
@@ -364,6 +367,7 @@ extern "C" int gibbs_load(gibbs_t *h, const int64_t *doc_ptr, const int32_t *wor
     CK(cudaStreamSynchronize(h->stream));
     h->loaded = true;
     h->sweep = 0;
+    h->hat_phi_set = h->hat_theta_set = false;
     h->st.ldk = h->ldk;
     h->st.max_active = max_a;
     // byte models: record 8 B read + 4 B z write-back, two 4-byte RMWs on the delta table, the row fetch,
@@ -509,8 +513,8 @@ static int merge_block(gibbs_handle *h) {
     int bx = std::min(256, (ldk4 + 31) / 32 * 32);
     int by = std::max(1, 256 / bx);
     dim3 block(bx, by);
-    unsigned grid = (unsigned)std::min<long long>((h->desc.V + by * 4 - 1) / (by * 4), (long long)h->sm_count * 8);
-    merge_delta_kernel<<<grid, block, 0, h->stream>>>(reinterpret_cast<int4 *>(h->n_wk.p), reinterpret_cast<int4 *>(h->delta_wk.p),
+    unsigned grid = (unsigned)std::min<long long>((h->desc.V + by * 4 - 1) / (by * 4), (long long)h->sm_count * 4);
+    merge_delta_kernel<<<grid, block, sizeof(int) * (size_t)h->ldk, h->stream>>>(reinterpret_cast<int4 *>(h->n_wk.p), reinterpret_cast<int4 *>(h->delta_wk.p),
                                                       h->n_k.p, h->desc.V, ldk4, h->desc.K);
     CK(cudaGetLastError());
     h->st.last_launches++;
@@ -652,7 +656,7 @@ extern "C" int gibbs_emit_phi(gibbs_t *h, double *phi_KV, int32_t smoothed) {
     }
     dim3 grid((V + 31) / 32, (K + 31) / 32), block(32, 8);
     emit_phi_kernel<<<grid, block, 0, h->stream>>>(h->n_wk.p, den, d_phi, V, K, h->ldk, h->desc.beta,
-                                                   (double)V * h->desc.beta, smoothed);
+                                                   (double)V * h->desc.beta, smoothed, 0, 0.0, 0.0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(phi_KV, d_phi, sizeof(double) * (size_t)K * V, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -683,9 +687,74 @@ extern "C" int gibbs_emit_theta_csr(gibbs_t *h, double *theta_act, int32_t smoot
     TRY(reserve(h, h->scratch, sizeof(double) * (size_t)h->n_lab));
     double *d_th = reinterpret_cast<double *>(h->scratch.p);
     const long long blocks = (D * 32 + 255) / 256;
-    emit_theta_csr_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->lab_ptr.p, h->n_dk_act.p, d_th, h->desc.alpha, smoothed);
+    emit_theta_csr_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->lab_ptr.p, h->n_dk_act.p, d_th, h->desc.alpha, smoothed,
+                                                                   0, 0.0, 0.0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(theta_act, d_th, sizeof(double) * (size_t)h->n_lab, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- thinning mean, perplexity
+extern "C" int gibbs_thin_accumulate(gibbs_t *h, double c_old, double c_new, int32_t smoothed, int32_t what) {
+    if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_thin_accumulate: corpus not loaded");
+    if (!(what & 3)) return fail(GIBBS_E_ARG, "gibbs_thin_accumulate: `what` selects neither phi (1) nor theta (2)");
+    CK(cudaSetDevice(h->desc.device));
+    const int K = h->desc.K, V = h->desc.V;
+    const long long D = h->desc.D;
+    if (what & 1) {
+        TRY(reserve(h, h->hat_phi, (size_t)K * V));
+        const int *den = h->n_k.p;
+        if (!smoothed) { TRY(column_sums(h, h->colsum.p)); den = h->colsum.p; }
+        dim3 grid((V + 31) / 32, (K + 31) / 32), block(32, 8);
+        emit_phi_kernel<<<grid, block, 0, h->stream>>>(h->n_wk.p, den, h->hat_phi.p, V, K, h->ldk, h->desc.beta,
+                                                       (double)V * h->desc.beta, smoothed, h->hat_phi_set ? 1 : 0, c_old, c_new);
+        CK(cudaGetLastError());
+        h->hat_phi_set = true;
+    }
+    if ((what & 2) && D > 0 && h->n_lab > 0) {
+        TRY(reserve(h, h->hat_theta, (size_t)h->n_lab));
+        const long long blocks = (D * 32 + 255) / 256;
+        emit_theta_csr_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->lab_ptr.p, h->n_dk_act.p, h->hat_theta.p, h->desc.alpha,
+                                                                       smoothed, h->hat_theta_set ? 1 : 0, c_old, c_new);
+        CK(cudaGetLastError());
+        h->hat_theta_set = true;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gibbs_thin_get(gibbs_t *h, double *ph_hat_KV, double *th_hat_act) {
+    if (!h || !h->loaded) return fail(GIBBS_E_STATE, "gibbs_thin_get: corpus not loaded");
+    CK(cudaSetDevice(h->desc.device));
+    if (ph_hat_KV) {
+        if (!h->hat_phi_set) return fail(GIBBS_E_STATE, "gibbs_thin_get: no phi sample accumulated yet");
+        CK(cudaMemcpyAsync(ph_hat_KV, h->hat_phi.p, sizeof(double) * (size_t)h->desc.K * h->desc.V, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (th_hat_act && h->n_lab > 0) {
+        if (!h->hat_theta_set) return fail(GIBBS_E_STATE, "gibbs_thin_get: no theta sample accumulated yet");
+        CK(cudaMemcpyAsync(th_hat_act, h->hat_theta.p, sizeof(double) * (size_t)h->n_lab, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gibbs_perplexity(gibbs_t *h, double *neg_log_sum, int64_t *n_pairs) {
+    if (!h || !h->loaded || !neg_log_sum) return fail(GIBBS_E_STATE, "gibbs_perplexity: corpus not loaded");
+    CK(cudaSetDevice(h->desc.device));
+    const long long D = h->desc.D;
+    *neg_log_sum = 0.0;
+    if (n_pairs) *n_pairs = h->N;
+    if (D == 0) return 0;
+    TRY(reserve(h, h->doc_sum, (size_t)D + 1));
+    const long long blocks = (D * 32 + 255) / 256;
+    perplexity_doc_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(D, h->work.p, h->lab_idx.p, h->n_dk_act.p, h->rec.p, h->n_wk.p,
+                                                                   h->n_k.p, h->ldk, h->desc.alpha, h->desc.beta,
+                                                                   (double)h->desc.V * h->desc.beta, h->doc_sum.p);
+    CK(cudaGetLastError());
+    sum_f64_kernel<<<1, 1024, 0, h->stream>>>(h->doc_sum.p, D, h->doc_sum.p + D);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(neg_log_sum, h->doc_sum.p + D, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -716,18 +785,149 @@ extern "C" int gibbs_hslda_set(gibbs_t *, int32_t, const double *, const double 
 }
 
 // ---------------------------------------------------------------------------------------------- test chains
-extern "C" int gibbs_test_chains(int32_t device, int32_t K, int32_t V, double alpha, const double *phi_KV,
-                                 int64_t D_test, const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
-                                 const int32_t *z_init, int32_t it, int32_t thinning, uint64_t seed, double *th_hat) {
-    if (!phi_KV || !doc_ptr || !word || !z_init || !th_hat) return fail(GIBBS_E_ARG, "gibbs_test_chains: null argument");
-    if (K <= 0 || V <= 0 || D_test < 0 || it < 0 || thinning <= 0) return fail(GIBBS_E_ARG, "gibbs_test_chains: bad sizes");
+struct gibbs_test_handle {
+    int device = 0, K = 0, V = 0, ldk = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    double *phiT = nullptr;
+    unsigned char *buf = nullptr;     // per-run staging, grows on demand
+    size_t cap = 0;
+};
+
+extern "C" int gibbs_test_create(gibbs_test_t **out, int32_t device, int32_t K, int32_t V, const double *phi_KV) {
+    if (!out || !phi_KV) return fail(GIBBS_E_ARG, "gibbs_test_create: null argument");
+    *out = nullptr;
+    if (K <= 0 || V <= 0) return fail(GIBBS_E_ARG, "gibbs_test_create: K and V must be positive");
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GIBBS_E_CUDA, "gibbs_test_chains: no CUDA device; this library has no CPU path");
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(GIBBS_E_CUDA, "gibbs_test_create: no CUDA device; this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(GIBBS_E_ARG, "gibbs_test_create: bad device ordinal");
     CK(cudaSetDevice(device));
-    int r = test_chains_run(K, V, alpha, phi_KV, D_test, doc_ptr, word, freq, z_init, it, thinning, seed, th_hat);
-    if (r == 1) return fail(GIBBS_E_STATE, "gibbs_test_chains: not implemented in this build");
-    if (r == -1) return fail(GIBBS_E_ARG, "gibbs_test_chains: K too large for the test kernel");
-    if (r) return fail(GIBBS_E_CUDA, std::string("gibbs_test_chains: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    gibbs_test_handle *t = new gibbs_test_handle();
+    t->device = device; t->K = K; t->V = V; t->ldk = (K + 3) / 4 * 4; t->sm_count = prop.multiProcessorCount;
+    double *tmp = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&t->phiT, sizeof(double) * (size_t)V * t->ldk);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&tmp, sizeof(double) * (size_t)K * V);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, phi_KV, sizeof(double) * (size_t)K * V, cudaMemcpyHostToDevice, t->stream);
+    if (e == cudaSuccess) {
+        dim3 grid((V + 31) / 32, (t->ldk + 31) / 32), block(32, 8);
+        transpose_phi_kernel<<<grid, block, 0, t->stream>>>(tmp, t->phiT, K, V, t->ldk);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) {
+        if (t->phiT) cudaFree(t->phiT);
+        if (t->stream) cudaStreamDestroy(t->stream);
+        delete t;
+        return cuda_fail(e, "gibbs_test_create", __FILE__, __LINE__);
+    }
+    *out = t;
+    return 0;
+}
+
+extern "C" void gibbs_test_destroy(gibbs_test_t *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaStreamSynchronize(t->stream);
+    if (t->phiT) cudaFree(t->phiT);
+    if (t->buf) cudaFree(t->buf);
+    cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+extern "C" int gibbs_test_run(gibbs_test_t *t, double alpha, double beta_fb, int64_t n_chains, const int64_t *doc_ptr,
+                              const int32_t *word, const int32_t *freq, const int64_t *lab_ptr, const int32_t *lab_idx,
+                              int32_t *z, int32_t init_mode, int32_t it, int32_t thinning, uint64_t seed,
+                              int64_t chain_base, double *th_hat) {
+    if (!t || !doc_ptr || !th_hat) return fail(GIBBS_E_ARG, "gibbs_test_run: null argument");
+    if (n_chains < 0 || it < 0 || thinning <= 0) return fail(GIBBS_E_ARG, "gibbs_test_run: bad sizes");
+    if (init_mode < GIBBS_TEST_INIT_GIVEN || init_mode > GIBBS_TEST_INIT_CASCADE) return fail(GIBBS_E_ARG, "gibbs_test_run: unknown init_mode");
+    if (init_mode == GIBBS_TEST_INIT_GIVEN && !z) return fail(GIBBS_E_ARG, "gibbs_test_run: init_mode GIVEN needs z");
+    if ((lab_ptr == nullptr) != (lab_idx == nullptr)) return fail(GIBBS_E_ARG, "gibbs_test_run: lab_ptr and lab_idx go together");
+    if (n_chains == 0) return 0;
+    if (doc_ptr[0] != 0 || (lab_ptr && lab_ptr[0] != 0)) return fail(GIBBS_E_ARG, "gibbs_test_run: CSR offsets must start at 0");
+    const long long N = doc_ptr[n_chains];
+    if (N > 0 && !word) return fail(GIBBS_E_ARG, "gibbs_test_run: null word array");
+    int amax = lab_ptr ? 0 : t->K;
+    for (int64_t c = 0; c < n_chains; ++c) {
+        if (doc_ptr[c + 1] < doc_ptr[c]) return fail(GIBBS_E_ARG, "gibbs_test_run: CSR offsets must be non-decreasing");
+        if (doc_ptr[c + 1] - doc_ptr[c] > 0x7fffffffLL) return fail(GIBBS_E_ARG, "gibbs_test_run: chain too long");
+        if (lab_ptr) {
+            const long long a = lab_ptr[c + 1] - lab_ptr[c];
+            if (a < 1 || a > t->K) return fail(GIBBS_E_ARG, "gibbs_test_run: a chain's topic list must have 1..K entries");
+            amax = std::max<int>(amax, (int)a);
+        }
+    }
+    for (long long i = 0; i < N; ++i)
+        if (word[i] < 0 || word[i] >= t->V) return fail(GIBBS_E_ARG, "gibbs_test_run: word id out of range");
+    const long long n_lab = lab_ptr ? lab_ptr[n_chains] : n_chains * (long long)t->K;
+    if (lab_ptr)
+        for (long long i = 0; i < n_lab; ++i)
+            if (lab_idx[i] < 0 || lab_idx[i] >= t->K) return fail(GIBBS_E_ARG, "gibbs_test_run: topic id out of range");
+    CK(cudaSetDevice(t->device));
+
+    // staging layout: doc_ptr | lab_ptr | th_out | word | freq | z | lab_idx | err
+    auto up8 = [](size_t x) { return (x + 7) / 8 * 8; };
+    size_t off = 0;
+    const size_t o_doc = off; off += sizeof(long long) * (size_t)(n_chains + 1);
+    const size_t o_labp = off; off += lab_ptr ? sizeof(long long) * (size_t)(n_chains + 1) : 0;
+    const size_t o_th = off; off += sizeof(double) * (size_t)std::max<long long>(n_lab, 1);
+    const size_t o_word = off; off += up8(sizeof(int) * (size_t)std::max<long long>(N, 1));
+    const size_t o_freq = off; off += freq ? up8(sizeof(int) * (size_t)std::max<long long>(N, 1)) : 0;
+    const size_t o_z = off; off += up8(sizeof(int) * (size_t)std::max<long long>(N, 1));
+    const size_t o_labi = off; off += lab_ptr ? up8(sizeof(int) * (size_t)n_lab) : 0;
+    const size_t o_err = off; off += 8;
+    if (off > t->cap) {
+        if (t->buf) { cudaFree(t->buf); t->buf = nullptr; t->cap = 0; }
+        CK(cudaMalloc((void **)&t->buf, off));
+        t->cap = off;
+    }
+    unsigned char *b = t->buf;
+    CK(cudaMemcpyAsync(b + o_doc, doc_ptr, sizeof(long long) * (size_t)(n_chains + 1), cudaMemcpyHostToDevice, t->stream));
+    if (lab_ptr) {
+        CK(cudaMemcpyAsync(b + o_labp, lab_ptr, sizeof(long long) * (size_t)(n_chains + 1), cudaMemcpyHostToDevice, t->stream));
+        CK(cudaMemcpyAsync(b + o_labi, lab_idx, sizeof(int) * (size_t)n_lab, cudaMemcpyHostToDevice, t->stream));
+    }
+    if (N) CK(cudaMemcpyAsync(b + o_word, word, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, t->stream));
+    if (N && freq) CK(cudaMemcpyAsync(b + o_freq, freq, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, t->stream));
+    if (N && init_mode == GIBBS_TEST_INIT_GIVEN) CK(cudaMemcpyAsync(b + o_z, z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, t->stream));
+    CK(cudaMemsetAsync(b + o_th, 0, sizeof(double) * (size_t)std::max<long long>(n_lab, 1), t->stream));
+    CK(cudaMemsetAsync(b + o_err, 0, 8, t->stream));
+
+    TestParams p{};
+    p.phiT = t->phiT; p.ldk = t->ldk; p.K = t->K; p.n_chains = n_chains;
+    p.doc_ptr = reinterpret_cast<const long long *>(b + o_doc);
+    p.word = reinterpret_cast<const int *>(b + o_word);
+    p.freq = freq ? reinterpret_cast<const int *>(b + o_freq) : nullptr;
+    p.lab_ptr = lab_ptr ? reinterpret_cast<const long long *>(b + o_labp) : nullptr;
+    p.lab_idx = lab_ptr ? reinterpret_cast<const int *>(b + o_labi) : nullptr;
+    p.z = reinterpret_cast<int *>(b + o_z);
+    p.th_out = reinterpret_cast<double *>(b + o_th);
+    p.alpha = alpha; p.beta_fb = beta_fb; p.it = it; p.thinning = thinning; p.init_mode = init_mode;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.chain_base = chain_base;
+    p.a_cap = (amax + 31) / 32 * 32;
+    p.err = reinterpret_cast<int *>(b + o_err);
+    const size_t per_warp = (size_t)p.a_cap * 16;
+    int wpc = (int)std::min<size_t>(8, (96 * 1024) / per_warp);
+    if (wpc < 1) {
+        wpc = 1;
+        if (per_warp > 227 * 1024) return fail(GIBBS_E_ARG, "gibbs_test_run: topic list too long for the shared-memory state (max ~14000 topics)");
+    }
+    const size_t smem = per_warp * wpc;
+    CK(cudaFuncSetAttribute(test_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ctas = (n_chains + wpc - 1) / wpc;
+    const unsigned grid = (unsigned)std::min<long long>(ctas, (long long)t->sm_count * 8);
+    test_chain_kernel<<<grid, wpc * 32, smem, t->stream>>>(p);
+    CK(cudaGetLastError());
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, b + o_err, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CK(cudaMemcpyAsync(th_hat, b + o_th, sizeof(double) * (size_t)n_lab, cudaMemcpyDeviceToHost, t->stream));
+    if (z && N) CK(cudaMemcpyAsync(z, b + o_z, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, t->stream));
+    CK(cudaStreamSynchronize(t->stream));
+    if (err) return fail(GIBBS_E_ARG, "gibbs_test_run: a z value is not in its chain's topic list");
     return 0;
 }
 

@@ -679,9 +679,16 @@ __global__ void export_z_kernel(long long n_work, const DocDesc *work, const lon
 // Thread (x, y) owns int4 column chunks x, x + blockDim.x, ... so its topic columns are fixed; four rows are in
 // flight per thread (both tables are read unconditionally) so the pass runs at memory speed; untouched 16-byte chunks
 // are not written.
+// The column sums of a block are first combined in shared memory (blockDim.y rows per column), so n_k sees one RED
+// per column per block instead of one per thread: K addresses sit in K/8 sectors and same-sector REDs serialise
+// in L2 (ncu r02a: 1.2 M REDs on 16 sectors were 90 % of this kernel's time).
 __global__ void __launch_bounds__(256) merge_delta_kernel(int4 *__restrict__ n_wk, int4 *__restrict__ delta,
                                                           int *__restrict__ n_k, long long V, int ldk4, int K) {
+    extern __shared__ int col_acc[];                 // [ldk4 * 4]
     const long long stride = (long long)gridDim.x * blockDim.y;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int q = tid; q < ldk4 * 4; q += nthr) col_acc[q] = 0;
+    __syncthreads();
     for (int c4 = threadIdx.x; c4 < ldk4; c4 += blockDim.x) {
         int4 acc = make_int4(0, 0, 0, 0);
         for (long long v0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; v0 < V; v0 += 4 * stride) {
@@ -705,16 +712,25 @@ __global__ void __launch_bounds__(256) merge_delta_kernel(int4 *__restrict__ n_w
             }
         }
         const int k = c4 * 4;
-        if (acc.x && k < K) atomicAdd(&n_k[k], acc.x);
-        if (acc.y && k + 1 < K) atomicAdd(&n_k[k + 1], acc.y);
-        if (acc.z && k + 2 < K) atomicAdd(&n_k[k + 2], acc.z);
-        if (acc.w && k + 3 < K) atomicAdd(&n_k[k + 3], acc.w);
+        if (acc.x) atomicAdd(&col_acc[k], acc.x);
+        if (acc.y) atomicAdd(&col_acc[k + 1], acc.y);
+        if (acc.z) atomicAdd(&col_acc[k + 2], acc.z);
+        if (acc.w) atomicAdd(&col_acc[k + 3], acc.w);
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nthr) {
+        const int a = col_acc[k];
+        if (a) atomicAdd(&n_k[k], a);
     }
 }
 
 // Column sums of the word-major table: out[k] += sum_v n_wk[v][k]  (= row sums of the reference's n_k_v).
 // Same thread layout as merge_delta_kernel; out must be zeroed by the caller.
 __global__ void column_sums_kernel(const int4 *__restrict__ n_wk, int *__restrict__ out, long long V, int ldk4, int K) {
+    extern __shared__ int col_acc[];                 // [ldk4 * 4]
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int q = tid; q < ldk4 * 4; q += nthr) col_acc[q] = 0;
+    __syncthreads();
     for (int c4 = threadIdx.x; c4 < ldk4; c4 += blockDim.x) {
         int4 acc = make_int4(0, 0, 0, 0);
         for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V;
@@ -723,18 +739,26 @@ __global__ void column_sums_kernel(const int4 *__restrict__ n_wk, int *__restric
             acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
         const int k = c4 * 4;
-        if (acc.x && k < K) atomicAdd(&out[k], acc.x);
-        if (acc.y && k + 1 < K) atomicAdd(&out[k + 1], acc.y);
-        if (acc.z && k + 2 < K) atomicAdd(&out[k + 2], acc.z);
-        if (acc.w && k + 3 < K) atomicAdd(&out[k + 3], acc.w);
+        if (acc.x) atomicAdd(&col_acc[k], acc.x);
+        if (acc.y) atomicAdd(&col_acc[k + 1], acc.y);
+        if (acc.z) atomicAdd(&col_acc[k + 2], acc.z);
+        if (acc.w) atomicAdd(&col_acc[k + 3], acc.w);
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nthr) {
+        const int a = col_acc[k];
+        if (a) atomicAdd(&out[k], a);
     }
 }
 
 // phi[k][v] from n_wk[v][k]: 32x32 tile transpose through shared memory.
 // smoothed: (n + beta) / (den[k] + V*beta) with den = n_k (LabeledLDA.py:231-234);
 // otherwise n / den[k] with den = column sums of the table (CascadeLDA.py:394-395; 0/0 -> NaN as in NumPy).
+// accumulate: phi = c_old * phi + c_new * current -- the thinning mean of LabeledLDA.py:143-144 / CascadeLDA.py:431-432,
+// one rounding per operation as NumPy evaluates it.
 __global__ void emit_phi_kernel(const int *__restrict__ n_wk, const int *__restrict__ den_k, double *__restrict__ phi,
-                                int V, int K, int ldk, double beta, double vbeta, int smoothed) {
+                                int V, int K, int ldk, double beta, double vbeta, int smoothed,
+                                int accumulate, double c_old, double c_new) {
     __shared__ int tile[32][33];
     const int v0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -748,7 +772,9 @@ __global__ void emit_phi_kernel(const int *__restrict__ n_wk, const int *__restr
             const int c = tile[threadIdx.x][r];
             const double den = smoothed ? __dadd_rn((double)den_k[k], vbeta) : (double)den_k[k];
             const double num = smoothed ? __dadd_rn((double)c, beta) : (double)c;
-            phi[(size_t)k * V + v] = __ddiv_rn(num, den);
+            double out = __ddiv_rn(num, den);
+            if (accumulate) out = __dadd_rn(__dmul_rn(c_old, phi[(size_t)k * V + v]), __dmul_rn(c_new, out));
+            phi[(size_t)k * V + v] = out;
         }
     }
 }
@@ -777,8 +803,9 @@ __global__ void emit_theta_kernel(long long D, const long long *lab_ptr, const i
 }
 
 // theta over the label lists only (the non-zero entries of LabeledLDA.py:236-239), aligned with lab_idx.
+// accumulate: thinning mean as in emit_phi_kernel (entries outside the label list stay 0 in the reference too).
 __global__ void emit_theta_csr_kernel(long long D, const long long *lab_ptr, const int *n_dk_act, double *theta_act,
-                                      double alpha, int smoothed) {
+                                      double alpha, int smoothed, int accumulate, double c_old, double c_new) {
     const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (d >= D) return;
@@ -791,8 +818,53 @@ __global__ void emit_theta_csr_kernel(long long D, const long long *lab_ptr, con
     }
     for (int j = lane; j < A; j += 32) {
         const double x = smoothed ? __dadd_rn((double)n_dk_act[lab0 + j], alpha) : (double)n_dk_act[lab0 + j];
-        theta_act[lab0 + j] = __ddiv_rn(x, den);
+        double out = __ddiv_rn(x, den);
+        if (accumulate) out = __dadd_rn(__dmul_rn(c_old, theta_act[lab0 + j]), __dmul_rn(c_new, out));
+        theta_act[lab0 + j] = out;
     }
+}
+
+// Training perplexity, LabeledLDA.py:256-265: per document the sum over its (unique) word ids of
+// -log(phi[:, w] . theta_d) with the smoothed phi / theta of get_phi / get_theta; theta_d is zero outside the label
+// list, so the inner product runs over the list.  One warp per work-list entry; out[doc] is written, never added to.
+__global__ void perplexity_doc_kernel(long long n_work, const DocDesc *work, const int *lab_idx, const int *n_dk_act,
+                                      const int2 *R, const int *n_wk, const int *n_k, int ldk, double alpha, double beta,
+                                      double vbeta, double *out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_work) return;
+    const DocDesc dd = work[w];
+    double den = 0.0;
+    for (int j = 0; j < dd.A; ++j) den = __dadd_rn(den, __dadd_rn((double)n_dk_act[dd.lab0 + j], alpha));
+    double acc = 0.0;
+    for (int i = lane; i < dd.len; i += 32) {
+        const int v = R[dd.rbase + (long long)i * dd.stride].x;
+        double dot = 0.0;
+        for (int j = 0; j < dd.A; ++j) {
+            const int k = lab_idx[dd.lab0 + j];
+            const double th = __ddiv_rn(__dadd_rn((double)n_dk_act[dd.lab0 + j], alpha), den);
+            const double ph = __ddiv_rn(__dadd_rn((double)n_wk[(size_t)v * ldk + k], beta), __dadd_rn((double)n_k[k], vbeta));
+            dot = __dadd_rn(dot, __dmul_rn(ph, th));
+        }
+        acc -= log(dot);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[dd.doc] = acc;
+}
+
+// Fixed-order sum of n doubles into out[0] (one block; thread t adds elements t, t + 1024, ... then a shared-memory tree).
+__global__ void __launch_bounds__(1024) sum_f64_kernel(const double *x, long long n, double *out) {
+    __shared__ double part[1024];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) a += x[i];
+    part[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = part[0];
 }
 
 __global__ void philox_kat_kernel(int n, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4) {

@@ -14,6 +14,7 @@
 #define GIBBS_STREAM_SWEEP 0u
 #define GIBBS_STREAM_INIT  1u
 #define GIBBS_STREAM_TEST  2u
+#define GIBBS_STREAM_TEST_INIT 4u
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

@@ -275,3 +275,125 @@ int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t
     free(delta_wk); free(delta_k);
     return err;
 }
+
+/* ------------------------------------------------------------------ frozen-phi test chains (fp64) */
+
+static void ks_scan32_f64(double *x) {
+    for (int off = 1; off < 32; off <<= 1) {
+        double y[32];
+        for (int j = 0; j < 32; ++j) y[j] = (j >= off) ? x[j] + x[j - off] : x[j];
+        memcpy(x, y, sizeof(y));
+    }
+}
+
+/* cum[] = running sums of w[0..A) in 32-wide Kogge-Stone chunks with a carry (the device order); returns cum[A-1]. */
+static double chunk_cumsum_f64(const double *w, int A, double *cum) {
+    double carry = 0.0;
+    int nch = (A + 31) / 32;
+    for (int c = 0; c < nch; ++c) {
+        double x[32];
+        for (int l = 0; l < 32; ++l) { int j = c * 32 + l; x[l] = (j < A) ? w[j] : 0.0; }
+        ks_scan32_f64(x);
+        for (int l = 0; l < 32; ++l) { int j = c * 32 + l; if (j < A) cum[j] = carry + x[l]; }
+        carry = carry + x[31];
+    }
+    return cum[A - 1];
+}
+
+static int pick_f64(const double *cum, int A, double thr) {
+    for (int j = 0; j < A; ++j) if (cum[j] > thr) return j;
+    return A - 1;
+}
+
+/* LabeledLDA.py:155-212 (prep4test + run_test) and CascadeLDA.py:186-247 (prep4test + cascade_test), one chain per
+ * (document, topic list); the draw at :172/:194 (:203/:233) is the inverse-CDF draw on the unnormalised weights.
+ * init_mode 0: z given (global topic ids); 1: LabeledLDA.prep4test; 2: CascadeLDA.prep4test.  Streams 4 (start
+ * state) and 2 (chain), counter (iteration, chain_base + chain, position). */
+int oracle_test_chains(int32_t K, int32_t V, const double *phi_KV, double alpha, double beta_fb, int64_t n_chains,
+                       const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
+                       const int64_t *lab_ptr, const int32_t *lab_idx, int32_t *z, int32_t init_mode,
+                       int32_t it, int32_t thinning, uint64_t seed, int64_t chain_base, double *th_hat) {
+    double *w = (double *)malloc(sizeof(double) * (size_t)K);
+    double *cum = (double *)malloc(sizeof(double) * (size_t)K);
+    int32_t *ndk = (int32_t *)malloc(sizeof(int32_t) * (size_t)K);
+    int32_t *lab = (int32_t *)malloc(sizeof(int32_t) * (size_t)K);
+    int rc = 0;
+    if (!w || !cum || !ndk || !lab) { rc = -2; goto done; }
+    for (int64_t c = 0; c < n_chains && !rc; ++c) {
+        int64_t n0 = doc_ptr[c];
+        int len = (int)(doc_ptr[c + 1] - n0);
+        int64_t l0 = lab_ptr ? lab_ptr[c] : c * (int64_t)K;
+        int A = lab_ptr ? (int)(lab_ptr[c + 1] - lab_ptr[c]) : K;
+        for (int j = 0; j < A; ++j) { lab[j] = lab_ptr ? lab_idx[l0 + j] : j; ndk[j] = 0; th_hat[l0 + j] = 0.0; }
+        int32_t *zc = z + n0;                                 /* list indices while the chain runs */
+        for (int n = 0; n < len; ++n) {                       /* start state */
+            int32_t v = word[n0 + n], f = freq ? freq[n0 + n] : 1;
+            int jn;
+            if (init_mode == 0) {
+                jn = find_label(lab, A, zc[n]);
+                if (jn < 0) { rc = -1; break; }
+            } else {
+                double total;
+                if (init_mode == 1) {
+                    for (int j = 0; j < A; ++j) w[j] = phi_KV[(size_t)lab[j] * V + v];          /* LabeledLDA.py:162,169 */
+                    total = chunk_cumsum_f64(w, A, cum);
+                } else {
+                    for (int j = 0; j < A; ++j) w[j] = phi_KV[(size_t)lab[j] * V + v] + beta_fb; /* CascadeLDA.py:194-195 */
+                    double colsum = chunk_cumsum_f64(w, A, cum);
+                    double first = 1.0 / (double)len;                                             /* :198 */
+                    for (int j = 0; j < A; ++j) w[j] = (j == 0) ? first : w[j] / colsum;          /* :196 */
+                    total = chunk_cumsum_f64(w, A, cum);
+                }
+                uint32_t x = oracle_draw_word(seed, 4u, 0u, (uint64_t)(chain_base + c), (uint64_t)n);
+                double u = ((double)x + 0.5) * (1.0 / 4294967296.0);
+                jn = pick_f64(cum, A, u * total);
+            }
+            zc[n] = jn;
+            ndk[jn] += f;                                     /* LabeledLDA.py:174-175 */
+        }
+        for (int i = 0; i < it && !rc; ++i) {                 /* LabeledLDA.py:184 */
+            for (int n = 0; n < len; ++n) {
+                int32_t v = word[n0 + n], f = freq ? freq[n0 + n] : 1;
+                int jo = zc[n];
+                ndk[jo] -= f;                                 /* :186 */
+                for (int j = 0; j < A; ++j) {
+                    double a = (double)ndk[j] + alpha;        /* :188 */
+                    w[j] = a * phi_KV[(size_t)lab[j] * V + v];/* :189-190 */
+                }
+                double total = chunk_cumsum_f64(w, A, cum);
+                if (total == 0.0 && beta_fb > 0.0) {          /* CascadeLDA.py:225-230 */
+                    for (int j = 0; j < A; ++j) {
+                        double a = (double)ndk[j] + alpha;
+                        double b = phi_KV[(size_t)lab[j] * V + v] + beta_fb;
+                        w[j] = a * b;
+                    }
+                    total = chunk_cumsum_f64(w, A, cum);
+                }
+                uint32_t x = oracle_draw_word(seed, 2u, (uint32_t)i, (uint64_t)(chain_base + c), (uint64_t)n);
+                double u = ((double)x + 0.5) * (1.0 / 4294967296.0);
+                int jn = pick_f64(cum, A, u * total);
+                zc[n] = jn;                                   /* :196 */
+                ndk[jn] += f;                                 /* :197 */
+            }
+            if ((i + 1) % thinning == 0) {                    /* :201-211 */
+                int s2 = (i + 1) / thinning;
+                long long sum = 0;
+                for (int j = 0; j < A; ++j) sum += ndk[j];
+                double den = (double)sum;
+                double c_old = (double)(s2 - 1) / (double)s2, c_new = 1.0 / (double)s2;
+                for (int j = 0; j < A; ++j) {
+                    double cur = (double)ndk[j] / den;
+                    if (s2 > 1) {
+                        double o = c_old * th_hat[l0 + j];
+                        double nw = c_new * cur;
+                        th_hat[l0 + j] = o + nw;
+                    } else th_hat[l0 + j] = cur;
+                }
+            }
+        }
+        for (int n = 0; n < len; ++n) zc[n] = lab[zc[n]];
+    }
+done:
+    free(w); free(cum); free(ndk); free(lab);
+    return rc;
+}

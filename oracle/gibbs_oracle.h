@@ -73,6 +73,13 @@ int oracle_llda_snapshot_sweep(int64_t n_tiles, const int64_t *tile_rng, int32_t
                                int32_t *n_wk, int32_t *n_dk_act, int32_t *n_k,
                                uint64_t seed, uint32_t sweep, uint64_t doc_base, int32_t n_threads);
 
+/* Frozen-phi test chains in fp64: LabeledLDA.py:155-212, CascadeLDA.py:186-247 (see include/gibbs_b200.h
+ * gibbs_test_run for the argument meaning; phi_KV is [K][V]). */
+int oracle_test_chains(int32_t K, int32_t V, const double *phi_KV, double alpha, double beta_fb, int64_t n_chains,
+                       const int64_t *doc_ptr, const int32_t *word, const int32_t *freq,
+                       const int64_t *lab_ptr, const int32_t *lab_idx, int32_t *z, int32_t init_mode,
+                       int32_t it, int32_t thinning, uint64_t seed, int64_t chain_base, double *th_hat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,9 @@ def load():
                                             i32p, i32p, i32p, u64, u32, u64]
     lib.oracle_llda_snapshot_sweep.argtypes = [i64, i64p, i32, i64p, i32p, i32p, i32p, i64p, i32p, i32, i32, i32,
                                                dbl, dbl, i32p, i32p, i32p, u64, u32, u64, i32]
+    lib.oracle_test_chains.argtypes = [i32, i32, f64p, dbl, dbl, i64, i64p, i32p, i32p, i64p, i32p, i32p, i32, i32, i32,
+                                       u64, i64, f64p]
+    lib.oracle_test_chains.restype = C.c_int
     for n in ("oracle_init_z", "oracle_counts_build", "oracle_llda_exact_sweep", "oracle_llda_snapshot_sweep"):
         getattr(lib, n).restype = C.c_int
     _lib = lib
@@ -179,3 +182,36 @@ class LldaOracle(object):
         labs[rows, self.lab_idx] = 1.0
         num = self.n_dk_dense() + labs * self.alpha
         return num / num.sum(axis=1)[:, None]
+
+
+def test_chains(phi_KV, doc_ptr, word, freq, it, thinning, alpha, lab_ptr=None, lab_idx=None, z_init=None, init="llda",
+                beta_fb=0.0, seed=0, chain_base=0):
+    """CPU restatement of gibbs_test_run -> (th_hat, z)."""
+    lib = load()
+    phi_KV = _a(phi_KV, np.float64)
+    K, V = phi_KV.shape
+    doc_ptr, word = _a(doc_ptr, np.int64), _a(word, np.int32)
+    freq = None if freq is None else _a(freq, np.int32)
+    n = doc_ptr.shape[0] - 1
+    if lab_ptr is not None:
+        lab_ptr, lab_idx = _a(lab_ptr, np.int64), _a(lab_idx, np.int32)
+        th = np.zeros(int(lab_ptr[-1]), dtype=np.float64)
+    else:
+        th = np.zeros((n, K), dtype=np.float64)
+    mode = {"given": 0, "llda": 1, "cascade": 2}[init]
+    z = _a(z_init, np.int32).copy() if mode == 0 else np.zeros(int(doc_ptr[-1]), dtype=np.int32)
+    rc = lib.oracle_test_chains(K, V, _p(phi_KV, f64p), float(alpha), float(beta_fb), n, _p(doc_ptr, i64p), _p(word, i32p),
+                                _p(freq, i32p), _p(lab_ptr, i64p), _p(lab_idx, i32p), _p(z, i32p), mode, int(it),
+                                int(thinning), int(seed), int(chain_base), _p(th, f64p))
+    if rc:
+        raise RuntimeError("oracle_test_chains failed (%d)" % rc)
+    return th, z
+test_chains.__test__ = False
+
+
+def perplexity(o):
+    """LabeledLDA.py:256-265 from an LldaOracle's counts (not weighted by f, as in the reference)."""
+    phi, theta = o.phi(), o.theta()
+    doc_of = np.repeat(np.arange(o.D), np.diff(o.doc_ptr))
+    dots = np.einsum("kn,nk->n", phi[:, o.word], theta[doc_of])
+    return float(np.exp(-np.log(dots).sum() / o.N))

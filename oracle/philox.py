@@ -33,6 +33,7 @@ STREAM_SWEEP = 0   # one word per training draw
 STREAM_INIT = 1    # one word per draw for device-side z initialisation
 STREAM_TEST = 2    # test-time (frozen phi) chains
 STREAM_HOST = 3    # host-side helpers (synthetic HSLDA state, ...)
+STREAM_TEST_INIT = 4   # start state of the test-time chains (prep4test)
 
 
 def philox4x32_10(ctr, key):
